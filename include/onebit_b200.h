@@ -1,0 +1,121 @@
+/*
+ * onebit_b200.h — C ABI of the B200-native OneBit 1-bit linear-layer path (libonebit_b200.so).
+ *
+ * The reference (xuyuzhuang11/OneBit @ 42d6d7b) has no FFI for this path: the hot path is the Python
+ * nn.Module `BitLinearInf` (transformers/src/transformers/models/bitnet.py:71-122) built from ATen ops.
+ * Each entry point below names the reference lines it replaces. All pointers are plain device (or,
+ * where stated, host) pointers; no torch types cross this boundary. `stream` is a cudaStream_t passed
+ * as void* (NULL = legacy default stream). Every function returns ONEBIT_OK (0) or a negative error
+ * code; onebit_last_error() returns the message of the calling thread's last failure.
+ *
+ * All device entry points are asynchronous on `stream`, perform no allocation and no host
+ * synchronisation, and are CUDA-graph capturable. Weights are read-only.
+ *
+ * Data layout (bitnet.py:78-80, scripts/convert_llama_to_infer_ckpt.py:7-15):
+ *   weight        int8  [N, K/8] row-major; column 8j+i of row n is bit i (LSB first) of byte (n, j);
+ *                       bit = 1 <=> sign = -1, bit = 0 <=> sign = +1.
+ *   weight_scale  [N]   (g)      input_factor [K] (h)      bias [N] or NULL
+ *   x             [M, K] row-major (M = product of the leading dims)   y [M, N]
+ */
+#ifndef ONEBIT_B200_H
+#define ONEBIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ONEBIT_API __attribute__((visibility("default")))
+#else
+#define ONEBIT_API
+#endif
+
+#define ONEBIT_OK 0
+#define ONEBIT_ERR_INVALID_ARGUMENT (-1) /* shape / dtype / alignment contract violated            */
+#define ONEBIT_ERR_CUDA (-2)             /* a CUDA runtime call or launch failed                    */
+#define ONEBIT_ERR_UNSUPPORTED_DEVICE (-3) /* not an sm_100 (B200) device                           */
+#define ONEBIT_ERR_WORKSPACE (-4)        /* workspace too small / NULL                              */
+
+typedef enum onebit_dtype {
+    ONEBIT_F16 = 0,
+    ONEBIT_BF16 = 1,
+    ONEBIT_F32 = 2
+} onebit_dtype;
+
+/* Kernel selection for onebit_bitlinear_forward (0 = automatic by M/K/N; others force one variant,
+ * used by tests and the bench to compare variants). */
+typedef enum onebit_variant {
+    ONEBIT_VARIANT_AUTO = 0,
+    ONEBIT_VARIANT_SIMT = 1, /* CUDA-core packed GEMV, any K % 8 == 0                                */
+    ONEBIT_VARIANT_MMA = 2,  /* bits -> fp16 fragments in registers -> mma.sync, small M             */
+    ONEBIT_VARIANT_TC5 = 3   /* tcgen05 + TMEM, large M (prefill)                                    */
+} onebit_variant;
+
+ONEBIT_API const char* onebit_version(void);
+ONEBIT_API const char* onebit_last_error(void);
+
+/* ONEBIT_OK iff `device` exists and is compute capability 10.x. */
+ONEBIT_API int onebit_device_check(int device);
+
+/* ---- bit layout ---------------------------------------------------------------------------------
+ * onebit_pack_signs   replaces fp16_to_int8, scripts/convert_llama_to_infer_ckpt.py:7-15:
+ *                     bit = (uint8)((1 - w)/2) for w in {+1,-1,0}; in general bit = 1 iff w <= -1.
+ * onebit_unpack_signs replaces BitLinearInf.int8_to_fp16, bitnet.py:98-110 (-2*bit + 1 in `dtype`).
+ * Requires K % 8 == 0. */
+ONEBIT_API int onebit_pack_signs(const void* w, int8_t* packed, int64_t n, int64_t k, int dtype, void* stream);
+ONEBIT_API int onebit_unpack_signs(const int8_t* packed, void* out, int64_t n, int64_t k, int dtype, void* stream);
+
+/* ---- forward ------------------------------------------------------------------------------------
+ * onebit_bitlinear_forward replaces BitLinearInf.forward, bitnet.py:112-122:
+ *     y = LayerNorm_N( g * ( S @ (h * x) ) ) (+ bias),  LayerNorm without affine, biased variance, eps.
+ * act_dtype: dtype of x and y. param_dtype: dtype of weight_scale / input_factor / bias.
+ * Requires K % 8 == 0, M >= 0, all pointers 16-byte aligned (torch allocations are).
+ * workspace: at least onebit_bitlinear_workspace_bytes(m, k, n) bytes of device memory. */
+ONEBIT_API size_t onebit_bitlinear_workspace_bytes(int64_t m, int64_t k, int64_t n);
+ONEBIT_API int onebit_bitlinear_forward(const void* x, const int8_t* weight, const void* weight_scale,
+                             const void* input_factor, const void* bias, void* y, int64_t m, int64_t k,
+                             int64_t n, int act_dtype, int param_dtype, float eps, void* workspace,
+                             size_t workspace_bytes, int variant, void* stream);
+
+/* The two halves of the forward, exposed for tensor-parallel shards and fused consumers
+ * (the LayerNorm of bitnet.py:118 is a reduction over the FULL N, so a row- or column-sharded
+ * layer must reduce across ranks between the halves — see DESIGN.md "Multi-GPU").
+ *   onebit_bitlinear_matvec : t = S @ (h * x), fp32 [M, N]; `scale_by_g` != 0 multiplies by g
+ *                             (bitnet.py:113-116). For a K-shard pass scale_by_g = 0, all-reduce t,
+ *                             then finish with onebit_scale_layernorm.
+ *   onebit_scale_layernorm  : y = LayerNorm_N(g * t) (+ bias); weight_scale == NULL means t is
+ *                             already scaled (bitnet.py:116-120). */
+ONEBIT_API int onebit_bitlinear_matvec(const void* x, const int8_t* weight, const void* weight_scale,
+                            const void* input_factor, float* t, int64_t m, int64_t k, int64_t n,
+                            int act_dtype, int param_dtype, int scale_by_g, int variant, void* stream);
+ONEBIT_API int onebit_scale_layernorm(const float* t, const void* weight_scale, const void* bias, void* y, int64_t m,
+                           int64_t n, int act_dtype, int param_dtype, float eps, void* stream);
+/* Column-parallel (N-sharded) LayerNorm: per-token partial sums (sum, sum of squares) of g*t over the
+ * local N rows -> stats[m][2] (fp64, so that sum-of-squares statistics stay exact enough), to be all-reduced (SUM), then onebit_layernorm_apply_stats with the global
+ * N. */
+ONEBIT_API int onebit_scale_partial_stats(const float* t, const void* weight_scale, double* stats, int64_t m, int64_t n,
+                               int param_dtype, void* stream);
+ONEBIT_API int onebit_layernorm_apply_stats(const float* t, const void* weight_scale, const void* bias,
+                                 const double* stats, void* y, int64_t m, int64_t n_local, int64_t n_global,
+                                 int act_dtype, int param_dtype, float eps, void* stream);
+
+/* ---- host-buffer convenience (what a non-torch caller binds; used for the end-to-end timing) -------
+ * A layer handle owns DEVICE copies of weight / weight_scale / input_factor / bias made from HOST
+ * buffers once (the reference's `model.to(cuda)`, evaluation/lm_eval.py:68), plus its workspace.
+ * onebit_layer_forward_host copies x host->device, runs the forward, copies y device->host and
+ * synchronises `stream` before returning. x_host / y_host should be pinned for full speed. */
+typedef struct onebit_layer onebit_layer;
+ONEBIT_API int onebit_layer_create(onebit_layer** out, const int8_t* weight_host, const void* weight_scale_host,
+                        const void* input_factor_host, const void* bias_host, int64_t k, int64_t n,
+                        int act_dtype, int param_dtype, float eps, int64_t max_m);
+ONEBIT_API int onebit_layer_forward_host(onebit_layer* layer, const void* x_host, void* y_host, int64_t m, void* stream);
+ONEBIT_API int onebit_layer_forward_device(onebit_layer* layer, const void* x_dev, void* y_dev, int64_t m, void* stream);
+ONEBIT_API void onebit_layer_destroy(onebit_layer* layer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONEBIT_B200_H */

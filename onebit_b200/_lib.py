@@ -1,0 +1,67 @@
+"""ctypes binding of libonebit_b200.so (the C ABI in include/onebit_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libonebit_b200.so"
+
+OK = 0
+F16, BF16, F32 = 0, 1, 2
+VARIANT_AUTO, VARIANT_SIMT, VARIANT_MMA, VARIANT_TC5 = 0, 1, 2, 3
+VARIANTS = {"auto": VARIANT_AUTO, "simt": VARIANT_SIMT, "mma": VARIANT_MMA, "tc5": VARIANT_TC5}
+
+_c = ctypes
+_vp, _i64, _int, _f32, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/onebit_b200.h declares (checked by tests)
+SIGNATURES = {
+    "onebit_version": (_c.c_char_p, []),
+    "onebit_last_error": (_c.c_char_p, []),
+    "onebit_device_check": (_int, [_int]),
+    "onebit_pack_signs": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
+    "onebit_unpack_signs": (_int, [_vp, _vp, _i64, _i64, _int, _vp]),
+    "onebit_bitlinear_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "onebit_bitlinear_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _vp, _sz,
+                                        _int, _vp]),
+    "onebit_bitlinear_matvec": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "onebit_scale_layernorm": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp]),
+    "onebit_scale_partial_stats": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    "onebit_layernorm_apply_stats": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _vp]),
+    "onebit_layer_create": (_int, [_c.POINTER(_vp), _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _f32, _i64]),
+    "onebit_layer_forward_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
+    "onebit_layer_forward_device": (_int, [_vp, _vp, _vp, _i64, _vp]),
+    "onebit_layer_destroy": (None, [_vp]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once). Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m onebit_b200.build` (nvcc, sm_100a). "
+                "onebit_b200 has no CPU or PyTorch fallback for the 1-bit linear path.")
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here means header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().onebit_last_error().decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")

@@ -1,0 +1,90 @@
+// Shared device/host helpers for libonebit_b200.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/onebit_b200.h"
+
+namespace onebit {
+
+// ---- error plumbing (thread-local message behind onebit_last_error) -------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define ONEBIT_CUDA_TRY(expr)                                                                      \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return ::onebit::fail(ONEBIT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+#define ONEBIT_REQUIRE(cond, msg)                                                 \
+    do {                                                                          \
+        if (!(cond)) return ::onebit::fail(ONEBIT_ERR_INVALID_ARGUMENT, (msg));   \
+    } while (0)
+
+inline size_t dtype_size(int dt) { return dt == ONEBIT_F32 ? 4 : 2; }
+inline bool dtype_ok(int dt) { return dt == ONEBIT_F16 || dt == ONEBIT_BF16 || dt == ONEBIT_F32; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// ---- dtype conversion -------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Dispatch a (runtime dtype) -> (template type) call. `F` is a generic lambda taking a value of the type.
+template <typename F>
+inline int dispatch_dtype(int dt, F&& f) {
+    switch (dt) {
+        case ONEBIT_F16: return f(__half{});
+        case ONEBIT_BF16: return f(__nv_bfloat16{});
+        case ONEBIT_F32: return f(float{});
+        default: return fail(ONEBIT_ERR_INVALID_ARGUMENT, "unknown dtype code " + std::to_string(dt));
+    }
+}
+
+// ---- kernel launchers implemented in the .cu files --------------------------------------------------
+// t[m][n] = sum_k sign(n,k) * h[k] * x[m][k]   (optionally * g[n]); fp32 output.
+int launch_matvec_simt(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m,
+                       int64_t k, int64_t n, int act_dtype, int param_dtype, bool scale_by_g, cudaStream_t s);
+bool matvec_mma_supported(int64_t m, int64_t k, int64_t n, int act_dtype);
+int launch_matvec_mma(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m,
+                      int64_t k, int64_t n, int act_dtype, int param_dtype, bool scale_by_g, cudaStream_t s);
+
+int launch_scale_layernorm(const float* t, const void* g, const void* bias, void* y, int64_t m, int64_t n,
+                           int act_dtype, int param_dtype, float eps, cudaStream_t s);
+int launch_scale_partial_stats(const float* t, const void* g, double* stats, int64_t m, int64_t n, int param_dtype,
+                               cudaStream_t s);
+int launch_layernorm_apply_stats(const float* t, const void* g, const void* bias, const double* stats, void* y,
+                                 int64_t m, int64_t n_local, int64_t n_global, int act_dtype, int param_dtype,
+                                 float eps, cudaStream_t s);
+int launch_pack(const void* w, int8_t* packed, int64_t n, int64_t k, int dtype, cudaStream_t s);
+int launch_unpack(const int8_t* packed, void* out, int64_t n, int64_t k, int dtype, cudaStream_t s);
+
+}  // namespace onebit
