@@ -1,7 +1,7 @@
 // C-ABI entry points of libonebit_b200.so (declared in include/onebit_b200.h): argument checking,
 // variant selection and the host-buffer layer handle. No torch types, no hidden global state apart
 // from a per-thread error string and a cached SM count.
-#include <mutex>
+#include <cstdlib>
 #include <new>
 
 #include "common.cuh"
@@ -14,6 +14,15 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ONEBIT_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 int num_sms() {
