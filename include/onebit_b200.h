@@ -50,7 +50,7 @@ typedef enum onebit_dtype {
 typedef enum onebit_variant {
     ONEBIT_VARIANT_AUTO = 0,
     ONEBIT_VARIANT_SIMT = 1, /* CUDA-core packed GEMV, any K % 8 == 0                                */
-    ONEBIT_VARIANT_MMA = 2,  /* bits -> fp16 fragments in registers -> mma.sync, small M             */
+    ONEBIT_VARIANT_MMA = 2,  /* bit-plane int8 mma.sync (IMMA), K % 256 == 0, M <= 8                  */
     ONEBIT_VARIANT_TC5 = 3   /* tcgen05 + TMEM, large M (prefill)                                    */
 } onebit_variant;
 
@@ -73,8 +73,10 @@ ONEBIT_API int onebit_unpack_signs(const int8_t* packed, void* out, int64_t n, i
  *     y = LayerNorm_N( g * ( S @ (h * x) ) ) (+ bias),  LayerNorm without affine, biased variance, eps.
  * act_dtype: dtype of x and y. param_dtype: dtype of weight_scale / input_factor / bias.
  * Requires K % 8 == 0, M >= 0, all pointers 16-byte aligned (torch allocations are).
- * workspace: at least onebit_bitlinear_workspace_bytes(m, k, n) bytes of device memory. */
+ * workspace: at least onebit_bitlinear_workspace_bytes(m, k, n) bytes of device memory (fp32 pre-LayerNorm
+ * tensor + the activation digits of the tensor-core variant), 16-byte aligned. */
 ONEBIT_API size_t onebit_bitlinear_workspace_bytes(int64_t m, int64_t k, int64_t n);
+ONEBIT_API size_t onebit_matvec_workspace_bytes(int64_t m, int64_t k);
 ONEBIT_API int onebit_bitlinear_forward(const void* x, const int8_t* weight, const void* weight_scale,
                              const void* input_factor, const void* bias, void* y, int64_t m, int64_t k,
                              int64_t n, int act_dtype, int param_dtype, float eps, void* workspace,
@@ -85,12 +87,14 @@ ONEBIT_API int onebit_bitlinear_forward(const void* x, const int8_t* weight, con
  * layer must reduce across ranks between the halves — see DESIGN.md "Multi-GPU").
  *   onebit_bitlinear_matvec : t = S @ (h * x), fp32 [M, N]; `scale_by_g` != 0 multiplies by g
  *                             (bitnet.py:113-116). For a K-shard pass scale_by_g = 0, all-reduce t,
- *                             then finish with onebit_scale_layernorm.
+ *                             then finish with onebit_scale_layernorm. workspace: at least
+ *                             onebit_matvec_workspace_bytes(m, k) bytes.
  *   onebit_scale_layernorm  : y = LayerNorm_N(g * t) (+ bias); weight_scale == NULL means t is
  *                             already scaled (bitnet.py:116-120). */
 ONEBIT_API int onebit_bitlinear_matvec(const void* x, const int8_t* weight, const void* weight_scale,
                             const void* input_factor, float* t, int64_t m, int64_t k, int64_t n,
-                            int act_dtype, int param_dtype, int scale_by_g, int variant, void* stream);
+                            int act_dtype, int param_dtype, int scale_by_g, void* workspace,
+                            size_t workspace_bytes, int variant, void* stream);
 ONEBIT_API int onebit_scale_layernorm(const float* t, const void* weight_scale, const void* bias, void* y, int64_t m,
                            int64_t n, int act_dtype, int param_dtype, float eps, void* stream);
 /* Column-parallel (N-sharded) LayerNorm: per-token partial sums (sum, sum of squares) of g*t over the

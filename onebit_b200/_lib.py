@@ -28,7 +28,9 @@ SIGNATURES = {
     "onebit_bitlinear_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "onebit_bitlinear_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _vp, _sz,
                                         _int, _vp]),
-    "onebit_bitlinear_matvec": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "onebit_matvec_workspace_bytes": (_sz, [_i64, _i64]),
+    "onebit_bitlinear_matvec": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _int, _vp, _sz, _int,
+                                       _vp]),
     "onebit_scale_layernorm": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _f32, _vp]),
     "onebit_scale_partial_stats": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "onebit_layernorm_apply_stats": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _vp]),

@@ -69,10 +69,12 @@ def bitlinear_matvec(x, weight, weight_scale, input_factor, scale_by_g: bool = T
     t = torch.empty((m, n), dtype=torch.float32, device=x.device)
     g = weight_scale.contiguous()
     h = input_factor.contiguous()
+    ws_bytes = lib.onebit_matvec_workspace_bytes(m, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         rc = lib.onebit_bitlinear_matvec(x2.data_ptr(), weight.data_ptr(), g.data_ptr(), h.data_ptr(), t.data_ptr(),
                                          m, k, n, _code(x.dtype, "activation"), _code(g.dtype, "parameter"),
-                                         int(scale_by_g), _lib.VARIANTS[variant], _stream(x))
+                                         int(scale_by_g), ws.data_ptr(), ws_bytes, _lib.VARIANTS[variant], _stream(x))
     _lib.check(rc, "onebit_bitlinear_matvec")
     return t.reshape(*x.shape[:-1], n)
 

@@ -60,7 +60,7 @@ static int pick_variant(int variant, int64_t m, int64_t k, int64_t n, int act_dt
             return ONEBIT_OK;
         case ONEBIT_VARIANT_MMA:
             ONEBIT_REQUIRE(matvec_mma_supported(m, k, n, act_dtype),
-                           "ONEBIT_VARIANT_MMA does not support this shape/dtype (needs K % 512 == 0)");
+                           "ONEBIT_VARIANT_MMA does not support this shape/dtype (needs K % 256 == 0, K <= 14336, M <= 8)");
             *chosen = variant;
             return ONEBIT_OK;
         case ONEBIT_VARIANT_TC5:
@@ -71,12 +71,16 @@ static int pick_variant(int variant, int64_t m, int64_t k, int64_t n, int act_dt
 }
 
 static int matvec_impl(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m, int64_t k,
-                       int64_t n, int act_dtype, int param_dtype, bool scale_by_g, int variant, cudaStream_t s) {
+                       int64_t n, int act_dtype, int param_dtype, bool scale_by_g, void* ws, size_t ws_bytes,
+                       int variant, cudaStream_t s) {
     int chosen = 0;
     int rc = pick_variant(variant, m, k, n, act_dtype, &chosen);
     if (rc != ONEBIT_OK) return rc;
-    if (chosen == ONEBIT_VARIANT_MMA)
-        return launch_matvec_mma(x, w, g, h, t, m, k, n, act_dtype, param_dtype, scale_by_g, s);
+    if (chosen == ONEBIT_VARIANT_MMA) {
+        if (m > 0 && (!ws || !aligned16(ws) || ws_bytes < matvec_mma_workspace_bytes(m, k)))
+            return fail(ONEBIT_ERR_WORKSPACE, "workspace missing, misaligned or smaller than onebit_matvec_workspace_bytes");
+        return launch_matvec_mma(x, w, g, h, t, m, k, n, act_dtype, param_dtype, scale_by_g, ws, s);
+    }
     return launch_matvec_simt(x, w, g, h, t, m, k, n, act_dtype, param_dtype, scale_by_g, s);
 }
 
@@ -117,20 +121,28 @@ int onebit_unpack_signs(const int8_t* packed, void* out, int64_t n, int64_t k, i
     return launch_unpack(packed, out, n, k, dtype, static_cast<cudaStream_t>(stream));
 }
 
+static size_t t_bytes(int64_t m, int64_t n) {  // t = S @ (h*x) in fp32, before scale + LayerNorm; 256-byte multiple
+    return (((size_t)m * (size_t)n * sizeof(float)) + 255) & ~(size_t)255;
+}
+
+size_t onebit_matvec_workspace_bytes(int64_t m, int64_t k) {
+    if (m <= 0 || k <= 0) return 16;
+    return matvec_mma_workspace_bytes(m, k);
+}
+
 size_t onebit_bitlinear_workspace_bytes(int64_t m, int64_t k, int64_t n) {
-    (void)k;
     if (m <= 0 || n <= 0) return 16;
-    return (size_t)m * (size_t)n * sizeof(float) + 16;  // t = S @ (h*x) in fp32, before scale + LayerNorm
+    return t_bytes(m, n) + onebit_matvec_workspace_bytes(m, k);
 }
 
 int onebit_bitlinear_matvec(const void* x, const int8_t* weight, const void* weight_scale, const void* input_factor,
                             float* t, int64_t m, int64_t k, int64_t n, int act_dtype, int param_dtype, int scale_by_g,
-                            int variant, void* stream) {
+                            void* workspace, size_t workspace_bytes, int variant, void* stream) {
     int rc = check_forward_args(x, weight, weight_scale, input_factor, t, m, k, n, act_dtype, param_dtype);
     if (rc != ONEBIT_OK) return rc;
     ONEBIT_REQUIRE(!scale_by_g || weight_scale, "scale_by_g set but weight_scale is NULL");
     return matvec_impl(x, weight, weight_scale, input_factor, t, m, k, n, act_dtype, param_dtype, scale_by_g != 0,
-                       variant, static_cast<cudaStream_t>(stream));
+                       workspace, workspace_bytes, variant, static_cast<cudaStream_t>(stream));
 }
 
 int onebit_scale_layernorm(const float* t, const void* weight_scale, const void* bias, void* y, int64_t m, int64_t n,
@@ -171,7 +183,7 @@ int onebit_bitlinear_forward(const void* x, const int8_t* weight, const void* we
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float* t = static_cast<float*>(workspace);
     rc = matvec_impl(x, weight, weight_scale, input_factor, t, m, k, n, act_dtype, param_dtype, /*scale_by_g=*/false,
-                     variant, s);
+                     static_cast<char*>(workspace) + t_bytes(m, n), workspace_bytes - t_bytes(m, n), variant, s);
     if (rc != ONEBIT_OK) return rc;
     return launch_scale_layernorm(t, weight_scale, bias, y, m, n, act_dtype, param_dtype, eps, s);
 }

@@ -75,8 +75,12 @@ inline int dispatch_dtype(int dt, F&& f) {
 int launch_matvec_simt(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m,
                        int64_t k, int64_t n, int act_dtype, int param_dtype, bool scale_by_g, cudaStream_t s);
 bool matvec_mma_supported(int64_t m, int64_t k, int64_t n, int act_dtype);
+size_t matvec_mma_workspace_bytes(int64_t m, int64_t k);
 int launch_matvec_mma(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m,
-                      int64_t k, int64_t n, int act_dtype, int param_dtype, bool scale_by_g, cudaStream_t s);
+                      int64_t k, int64_t n, int act_dtype, int param_dtype, bool scale_by_g, void* workspace,
+                      cudaStream_t s);
+int launch_quantize_tokens(const void* x, const void* h, uint8_t* digits, void* qmeta, int64_t m, int64_t k,
+                           int act_dtype, int param_dtype, cudaStream_t s);
 
 int launch_scale_layernorm(const float* t, const void* g, const void* bias, void* y, int64_t m, int64_t n,
                            int act_dtype, int param_dtype, float eps, cudaStream_t s);

@@ -34,8 +34,10 @@ def variants_for(m, k, n, dtype=torch.float16):
     w = torch.zeros(n * k // 8, dtype=torch.int8, device=dev())
     g = torch.ones(max(n, k), dtype=dtype, device=dev())
     code = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}[dtype]
+    wsb = lib.onebit_matvec_workspace_bytes(max(m, 1), k)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev())
     rc = lib.onebit_bitlinear_matvec(x.data_ptr(), w.data_ptr(), g.data_ptr(), g.data_ptr(), t.data_ptr(), m, k, n,
-                                     code, code, 0, _lib.VARIANT_MMA, None)
+                                     code, code, 0, ws.data_ptr(), wsb, _lib.VARIANT_MMA, None)
     torch.cuda.synchronize()
     if rc == 0:
         out.append("mma")

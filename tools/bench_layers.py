@@ -31,6 +31,9 @@ def time_shape(k, n, m, variant, use_graph, peak):
     x = torch.randn(m, k, device=dev).half()
     lib = _lib.load()
     t = torch.empty(m, n, dtype=torch.float32, device=dev)
+    wsb = lib.onebit_bitlinear_workspace_bytes(m, k, n)
+    wsp = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    mwsb = lib.onebit_matvec_workspace_bytes(m, k)
     y = torch.empty(m, n, dtype=torch.float16, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     var = _lib.VARIANTS[variant]
@@ -39,11 +42,10 @@ def time_shape(k, n, m, variant, use_graph, peak):
         for w in ws:
             if which == "matvec":
                 rc = lib.onebit_bitlinear_matvec(x.data_ptr(), w.data_ptr(), g.data_ptr(), h.data_ptr(), t.data_ptr(), m,
-                                                 k, n, 0, 0, 0, var, stream)
+                                                 k, n, 0, 0, 0, wsp.data_ptr(), mwsb, var, stream)
             else:
                 rc = lib.onebit_bitlinear_forward(x.data_ptr(), w.data_ptr(), g.data_ptr(), h.data_ptr(), None,
-                                                  y.data_ptr(), m, k, n, 0, 0, 1e-5, t.data_ptr(), t.numel() * 4 + 16,
-                                                  var, stream)
+                                                  y.data_ptr(), m, k, n, 0, 0, 1e-5, wsp.data_ptr(), wsb, var, stream)
             assert rc == 0, _lib.last_error()
 
     out = {}
