@@ -119,6 +119,64 @@ ONEBIT_API int onebit_layer_forward_host(onebit_layer* layer, const void* x_host
 ONEBIT_API int onebit_layer_forward_device(onebit_layer* layer, const void* x_dev, void* y_dev, int64_t m, void* stream);
 ONEBIT_API void onebit_layer_destroy(onebit_layer* layer);
 
+/* ---- fused decode step (the callers either side of the hot path) -------------------
+ * One decode step of the reference's BitLlamaForCausalLMInf (modeling_bitllama.py:1512-1675) for `batch`
+ * sequences with a static KV cache: embedding (:1202), per layer RMSNorm (:67-81) -> q/k/v BitLinearInf
+ * (:522-524) -> RoPE (:176-181) -> attention over the cache (:543-563) -> o_proj (:580) -> residual ->
+ * RMSNorm -> gate/up BitLinearInf -> SiLU*up -> down_proj (:257) -> residual; final RMSNorm (:1315), lm_head
+ * (:1610) and greedy argmax (generation/utils.py:2540). Every BitLinear runs through the bit-plane IMMA GEMV;
+ * the glue between them (LayerNorm of bitnet.py:118, residual adds, norms, activation quantisation) is fused
+ * into small kernels, so one step is ~9 launches per layer and is CUDA-graph capturable (position and token ids
+ * live in device memory and are advanced on the device).
+ * All pointers in the parameter structs are DEVICE pointers that must outlive the decoder. Floating-point
+ * parameters (weight_scale, input_factor, norm weights) are `param_dtype`; embed_tokens / lm_head are fp16. */
+typedef struct onebit_bitlinear_params {
+    const int8_t* weight;        /* [N, K/8] packed signs */
+    const void* weight_scale;    /* [N] */
+    const void* input_factor;    /* [K] */
+} onebit_bitlinear_params;
+
+typedef struct onebit_layer_params {
+    onebit_bitlinear_params q, k, v, o, gate, up, down;
+    const void* input_layernorm;           /* [hidden] RMSNorm weight */
+    const void* post_attention_layernorm;  /* [hidden] */
+} onebit_layer_params;
+
+typedef struct onebit_decoder_config {
+    int hidden_size, intermediate_size, num_layers, num_heads, vocab_size, max_seq_len, max_batch;
+    int param_dtype;   /* onebit_dtype of weight_scale / input_factor / norm weights */
+    float rms_eps;     /* config.rms_norm_eps */
+    float ln_eps;      /* 1e-5, nn.LayerNorm default inside BitLinearInf */
+    /* tensor parallelism (1 = none). With tp_size > 1 the decoder holds the rank's shard: q/k/v/gate/up are
+     * row (N) shards, o/down are byte-column (K) shards; the caller provides an all-reduce callback. */
+    int tp_size, tp_rank;
+} onebit_decoder_config;
+
+/* All-reduce (SUM, in place) of `count` fp32 values on `stream`, supplied by the host (NCCL in production,
+ * nothing when tp_size == 1). Must be stream-ordered and capturable. */
+typedef int (*onebit_allreduce_fn)(void* user, float* data, int64_t count, void* stream);
+
+typedef struct onebit_decoder onebit_decoder;
+ONEBIT_API int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg,
+                                     const onebit_layer_params* layers, const void* embed_tokens_f16,
+                                     const void* final_norm, const void* lm_head_f16, const float* rope_cos,
+                                     const float* rope_sin, onebit_allreduce_fn allreduce, void* allreduce_user);
+/* Set the device-resident state: token ids to feed next [batch] and their positions [batch]. Host pointers. */
+ONEBIT_API int onebit_decoder_reset(onebit_decoder* dec, const int64_t* ids_host, const int32_t* pos_host, int batch,
+                                    void* stream);
+/* One step for `batch` sequences: consumes the device-resident ids/positions, writes logits (fp32
+ * [batch, vocab], device, optional) and leaves next ids (argmax) + advanced positions on the device.
+ * `forced_ids_dev` (optional, device int64 [batch]) overrides the fed ids (teacher forcing / prompt). */
+ONEBIT_API int onebit_decoder_step(onebit_decoder* dec, int batch, const int64_t* forced_ids_dev, float* logits_dev,
+                                   void* stream);
+/* Host-buffer step for the end-to-end timing: ids from host (pinned), next ids back to host, synchronises. */
+ONEBIT_API int onebit_decoder_step_host(onebit_decoder* dec, int batch, const int64_t* ids_host,
+                                        int64_t* next_ids_host, void* stream);
+ONEBIT_API const int64_t* onebit_decoder_next_ids(onebit_decoder* dec);  /* device int64 [max_batch] */
+ONEBIT_API const int32_t* onebit_decoder_positions(onebit_decoder* dec); /* device int32 [max_batch] */
+ONEBIT_API int onebit_decoder_kernel_launches_per_step(onebit_decoder* dec);
+ONEBIT_API void onebit_decoder_destroy(onebit_decoder* dec);
+
 #ifdef __cplusplus
 }
 #endif

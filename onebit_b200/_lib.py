@@ -38,7 +38,30 @@ SIGNATURES = {
     "onebit_layer_forward_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "onebit_layer_forward_device": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "onebit_layer_destroy": (None, [_vp]),
+    "onebit_decoder_create": (_int, [_c.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "onebit_decoder_reset": (_int, [_vp, _vp, _vp, _int, _vp]),
+    "onebit_decoder_step": (_int, [_vp, _int, _vp, _vp, _vp]),
+    "onebit_decoder_step_host": (_int, [_vp, _int, _vp, _vp, _vp]),
+    "onebit_decoder_next_ids": (_vp, [_vp]),
+    "onebit_decoder_positions": (_vp, [_vp]),
+    "onebit_decoder_kernel_launches_per_step": (_int, [_vp]),
+    "onebit_decoder_destroy": (None, [_vp]),
 }
+
+
+class BitLinearParams(_c.Structure):
+    _fields_ = [("weight", _vp), ("weight_scale", _vp), ("input_factor", _vp)]
+
+
+class LayerParams(_c.Structure):
+    _fields_ = [(n, BitLinearParams) for n in ("q", "k", "v", "o", "gate", "up", "down")] + [
+        ("input_layernorm", _vp), ("post_attention_layernorm", _vp)]
+
+
+class DecoderConfig(_c.Structure):
+    _fields_ = [(n, _int) for n in ("hidden_size", "intermediate_size", "num_layers", "num_heads", "vocab_size",
+                                    "max_seq_len", "max_batch", "param_dtype")] + [
+        ("rms_eps", _f32), ("ln_eps", _f32), ("tp_size", _int), ("tp_rank", _int)]
 
 _lib = None
 

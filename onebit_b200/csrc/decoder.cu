@@ -1,0 +1,598 @@
+// Fused decode step around the bit-plane IMMA GEMV — the callers either side of the hot path
+// (SURVEY.md §8f-1). Mirrors one q_len = 1 forward of the reference's BitLlamaForCausalLMInf
+// (transformers/src/transformers/models/bitllama/modeling_bitllama.py):
+//   embed_tokens :1202 | LlamaRMSNorm :67-81 | q/k/v :522-524 | RoPE :176-181 | cache + attention :536-563 |
+//   o_proj :580 | residual :912 | MLP down(silu(gate) * up) :257 | final norm :1315 | lm_head :1610 |
+//   greedy argmax generation/utils.py:2540
+// Every BitLinearInf (bitnet.py:112-122) = IMMA GEMV (imma_gemv.cuh) + the LayerNorm of bitnet.py:118, whose
+// statistics come from per-CTA partial sums the GEMV emits and are applied in the consumer's prologue.
+//
+// Kernels per layer (9): glue(resid+norm -> q/k/v digits) | GEMV qkv | attention | glue(o digits) | GEMV o |
+// glue(resid+norm -> gate/up digits) | GEMV gate,up | glue(silu*up -> down digits) | GEMV down.
+// All state that changes between steps (token ids, positions) lives in device memory, so a step is one
+// CUDA graph replay. The residual stream is kept in fp32.
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "imma_gemv.cuh"
+
+namespace onebit {
+
+int launch_imma_gemv(const imma::Args& a, int param_dtype, cudaStream_t s);  // matvec_mma.cu
+
+namespace {
+
+using imma::QMeta;
+constexpr int kGlueThreads = 512;
+constexpr int kHeadDim = 128;
+
+enum GlueMode {
+    GLUE_EMBED_NORM = 0,   // resid_out = embed[ids];                x = RMSNorm(resid_out) * ln_w
+    GLUE_RESID_NORM = 1,   // resid_out = resid_in + LN_a(t_a);      x = RMSNorm(resid_out) * ln_w
+    GLUE_SILU_MUL = 2,     // x = silu(LN_a(t_a)) * LN_b(t_b)
+    GLUE_PLAIN = 3,        // x = x_plain
+};
+
+struct GlueArgs {
+    int mode, M, K, nprob, write_x_f16;
+    const float* t_a; const float* stats_a; int ncta_a;   // previous GEMV output (already * g), [ncta][M][2] partials
+    const float* t_b; const float* stats_b; int ncta_b;
+    const float* resid_in; float* resid_out;              // [M][K] fp32
+    const __half* embed; const long long* ids;            // GLUE_EMBED_NORM
+    const void* ln_w;                                      // RMSNorm weight (TP)
+    const float* x_plain;
+    float ln_eps, rms_eps;
+    const void* h[3]; uint8_t* digits[3]; QMeta* qmeta[3];  // per problem: input_factor, outputs
+    __half* x_f16;                                          // optional [M][K] (lm_head input)
+};
+
+__device__ __forceinline__ float block_sum_f(float v, float* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+    return r;
+}
+
+// mean / rstd of a BitLinear output over its N rows from the GEMV's per-CTA (sum, sum sq) partials.
+__device__ __forceinline__ void ln_stats(const float* stats, int ncta, int M, int m, int n_rows, float eps,
+                                         float* sh2, float& mean, float& rstd) {
+    // warp 0 sums the partials in double (<= a few hundred values), broadcast through shared memory
+    if (threadIdx.x < 32) {
+        double s = 0.0, q = 0.0;
+        for (int c = threadIdx.x; c < ncta; c += 32) {
+            const float2 p = *reinterpret_cast<const float2*>(stats + ((size_t)c * M + m) * 2);
+            s += (double)p.x;
+            q += (double)p.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (threadIdx.x == 0) {
+            const double mu = s / (double)n_rows;
+            const double var = fmax(q / (double)n_rows - mu * mu, 0.0);  // biased variance (nn.LayerNorm)
+            sh2[0] = (float)mu;
+            sh2[1] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
+    __syncthreads();
+    mean = sh2[0];
+    rstd = sh2[1];
+    __syncthreads();
+}
+
+// One CTA per (token, problem): builds x (the BitLinear input) in shared memory, then quantises h_p * x.
+template <typename TP>
+__global__ void __launch_bounds__(kGlueThreads) glue_kernel(const __grid_constant__ GlueArgs A) {
+    extern __shared__ __align__(16) float xs[];  // [K]
+    __shared__ float sh[kGlueThreads / 32];
+    __shared__ float sh2[2];
+    __shared__ long long scratch[kGlueThreads / 32];
+    imma::pdl_launch_dependents();
+    imma::pdl_wait();
+    const int m = blockIdx.x, p = blockIdx.y, K = A.K;
+    const TP* lnw = static_cast<const TP*>(A.ln_w);
+
+    if (A.mode == GLUE_EMBED_NORM || A.mode == GLUE_RESID_NORM) {
+        float mean = 0.f, rstd = 0.f;
+        if (A.mode == GLUE_RESID_NORM) ln_stats(A.stats_a, A.ncta_a, A.M, m, K, A.ln_eps, sh2, mean, rstd);
+        float ss = 0.f;
+        for (int k = threadIdx.x; k < K; k += kGlueThreads) {
+            float r;
+            if (A.mode == GLUE_EMBED_NORM)
+                r = __half2float(A.embed[(size_t)A.ids[m] * K + k]);
+            else
+                r = A.resid_in[(size_t)m * K + k] + (A.t_a[(size_t)m * K + k] - mean) * rstd;  // bitnet.py:118 + :912
+            if (p == 0) A.resid_out[(size_t)m * K + k] = r;
+            xs[k] = r;
+            ss += r * r;
+        }
+        const float var = block_sum_f(ss, sh) / (float)K;           // LlamaRMSNorm :77
+        const float rr = rsqrtf(var + A.rms_eps);
+        for (int k = threadIdx.x; k < K; k += kGlueThreads) xs[k] = xs[k] * rr * to_f32(lnw[k]);
+    } else if (A.mode == GLUE_SILU_MUL) {
+        float mean_a, rstd_a, mean_b, rstd_b;
+        ln_stats(A.stats_a, A.ncta_a, A.M, m, K, A.ln_eps, sh2, mean_a, rstd_a);
+        ln_stats(A.stats_b, A.ncta_b, A.M, m, K, A.ln_eps, sh2, mean_b, rstd_b);
+        for (int k = threadIdx.x; k < K; k += kGlueThreads) {
+            const float a = (A.t_a[(size_t)m * K + k] - mean_a) * rstd_a;
+            const float b = (A.t_b[(size_t)m * K + k] - mean_b) * rstd_b;
+            xs[k] = a / (1.f + expf(-a)) * b;  // act_fn(gate) * up, modeling_bitllama.py:257
+        }
+    } else {
+        for (int k = threadIdx.x; k < K; k += kGlueThreads) xs[k] = A.x_plain[(size_t)m * K + k];
+    }
+    __syncthreads();
+    if (A.write_x_f16) {
+        if (p == 0)
+            for (int k = threadIdx.x; k < K; k += kGlueThreads) A.x_f16[(size_t)m * K + k] = __float2half_rn(xs[k]);
+        return;
+    }
+    // x' = h_p * x (bitnet.py:113), amax, digits
+    const TP* h = static_cast<const TP*>(A.h[p]);
+    float am = 0.f;
+    for (int k = threadIdx.x; k < K; k += kGlueThreads) {
+        const float v = xs[k] * to_f32(h[k]);
+        xs[k] = v;
+        am = fmaxf(am, fabsf(v));
+    }
+    __syncthreads();
+    imma::quantize_from_smem(xs, K, am, A.digits[p] + (size_t)m * (K / imma::kUnitCols) * imma::kUnitBytes,
+                             A.qmeta[p] + m, scratch);
+}
+
+// ---- attention for one new token per sequence: LN(q,k,v) -> RoPE -> cache append -> softmax(QK^T/sqrt(d)) V ----
+struct AttnArgs {
+    const float* t_q; const float* t_k; const float* t_v;  // [M][H] fp32 (already * g)
+    const float* stats_q; const float* stats_k; const float* stats_v; int ncta;  // per-CTA partials of each projection
+    int M, H, n_heads, max_seq;
+    const int* pos;                 // [M] device
+    const float* rope_cos; const float* rope_sin;  // [max_seq][kHeadDim/2]
+    __half* kcache; __half* vcache; // [M_max][n_heads][max_seq][kHeadDim] for this layer
+    float* out;                     // [M][H] fp32
+    float ln_eps;
+};
+
+__global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ AttnArgs A) {
+    extern __shared__ __align__(16) float sc[];  // [T] scores
+    __shared__ float qs[kHeadDim];
+    __shared__ float sh2[2];
+    __shared__ float red[kHeadDim / 32];
+    imma::pdl_launch_dependents();
+    imma::pdl_wait();
+    const int m = blockIdx.x, hd = blockIdx.y, d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    const int pos = A.pos[m], T = pos + 1;
+    float mq, rq, mk, rk, mv, rv;
+    ln_stats(A.stats_q, A.ncta, A.M, m, A.H, A.ln_eps, sh2, mq, rq);
+    ln_stats(A.stats_k, A.ncta, A.M, m, A.H, A.ln_eps, sh2, mk, rk);
+    ln_stats(A.stats_v, A.ncta, A.M, m, A.H, A.ln_eps, sh2, mv, rv);
+    const size_t col = (size_t)m * A.H + hd * kHeadDim;
+    const int half = kHeadDim / 2, dp = d < half ? d + half : d - half, fi = d < half ? d : d - half;
+    const float c = A.rope_cos[(size_t)pos * half + fi], s = A.rope_sin[(size_t)pos * half + fi];
+    const float q0 = (A.t_q[col + d] - mq) * rq, q1 = (A.t_q[col + dp] - mq) * rq;
+    const float k0 = (A.t_k[col + d] - mk) * rk, k1 = (A.t_k[col + dp] - mk) * rk;
+    // rotate_half: (-x2, x1)  (modeling_bitllama.py:168-181)
+    const float qr = d < half ? q0 * c - q1 * s : q0 * c + q1 * s;
+    const float kr = d < half ? k0 * c - k1 * s : k0 * c + k1 * s;
+    const float vv = (A.t_v[col + d] - mv) * rv;
+    __half* kc = A.kcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
+    __half* vc = A.vcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
+    kc[(size_t)pos * kHeadDim + d] = __float2half_rn(kr);
+    vc[(size_t)pos * kHeadDim + d] = __float2half_rn(vv);
+    qs[d] = qr * 0.08838834764831845f;  // 1/sqrt(128), :546
+    __syncthreads();
+    // scores: one warp per cached position, lanes over d (4 each)
+    const float4 qv = *reinterpret_cast<const float4*>(&qs[4 * lane]);
+    for (int j = warp; j < T; j += kHeadDim / 32) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(kc + (size_t)j * kHeadDim + 4 * lane);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        float dot = qv.x * a.x + qv.y * a.y + qv.z * b.x + qv.w * b.y;
+        dot = warp_sum(dot);
+        if (lane == 0) sc[j] = dot;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = d; j < T; j += kHeadDim) mx = fmaxf(mx, sc[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = d; j < T; j += kHeadDim) {
+        const float e = expf(sc[j] - mx);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) acc += sc[j] * __half2float(vc[(size_t)j * kHeadDim + d]);
+    A.out[col + d] = acc * inv;
+}
+
+// ---- lm_head: logits[m][v] = sum_k W[v][k] * x[m][k], fp16 weights, fp32 accumulate (:1610-1611) ----
+template <int MT>
+__global__ void __launch_bounds__(256) lm_head_kernel(const __half* __restrict__ W, const __half* __restrict__ x,
+                                                      float* __restrict__ logits, int V, int H, int M) {
+    extern __shared__ __align__(16) __half xsh[];  // [M][H]
+    imma::pdl_launch_dependents();
+    imma::pdl_wait();
+    for (int i = threadIdx.x; i < M * H / 8; i += 256)
+        reinterpret_cast<uint4*>(xsh)[i] = reinterpret_cast<const uint4*>(x)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = blockIdx.x * 8 + warp;
+    if (v >= V) return;
+    float acc[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+    const uint4* wr = reinterpret_cast<const uint4*>(W + (size_t)v * H);
+    for (int i = lane; i < H / 8; i += 32) {
+        uint4 wv;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(wv.x), "=r"(wv.y), "=r"(wv.z), "=r"(wv.w) : "l"(wr + i));
+        const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            if (m < M) {
+                const uint4 xv = reinterpret_cast<const uint4*>(xsh + (size_t)m * H)[i];
+                const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 a = __half22float2(w2[q]), b = __half22float2(x2[q]);
+                    acc[m] += a.x * b.x + a.y * b.y;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const float r = warp_sum(acc[m]);
+        if (lane == 0 && m < M) logits[(size_t)m * V + v] = r;
+    }
+}
+
+// greedy argmax (first maximum wins, like torch.argmax on ties in practice) + advance ids / positions
+__global__ void __launch_bounds__(1024) argmax_advance_kernel(const float* __restrict__ logits, int V,
+                                                             long long* __restrict__ ids, int* __restrict__ pos) {
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    imma::pdl_launch_dependents();
+    imma::pdl_wait();
+    const int m = blockIdx.x;
+    const float* row = logits + (size_t)m * V;
+    float best = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int v = threadIdx.x; v < V; v += 1024) {
+        const float x = row[v];
+        if (x > best) { best = x; idx = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w)
+            if (bv[w] > best || (bv[w] == best && bi[w] < idx)) { best = bv[w]; idx = bi[w]; }
+        ids[m] = idx;
+        pos[m] += 1;
+    }
+}
+
+__global__ void copy_ids_kernel(const long long* src, long long* dst, int n) {
+    imma::pdl_launch_dependents();
+    imma::pdl_wait();
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    ONEBIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args...));
+    return ONEBIT_OK;
+}
+
+}  // namespace
+}  // namespace onebit
+
+using namespace onebit;
+
+struct onebit_decoder {
+    onebit_decoder_config cfg;
+    std::vector<onebit_layer_params> layers;
+    const __half* embed = nullptr;
+    const void* final_norm = nullptr;
+    const __half* lm_head = nullptr;
+    const float* rope_cos = nullptr;
+    const float* rope_sin = nullptr;
+    onebit_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    // device state / scratch (one cudaMalloc arena)
+    char* arena = nullptr;
+    float* resid[2] = {nullptr, nullptr};
+    float *t_qkv = nullptr, *t_o = nullptr, *t_gu = nullptr, *t_d = nullptr, *attn_out = nullptr, *logits = nullptr;
+    float *st_qkv = nullptr, *st_o = nullptr, *st_gu = nullptr, *st_d = nullptr;
+    uint8_t *dg_qkv = nullptr, *dg_o = nullptr, *dg_gu = nullptr, *dg_d = nullptr;
+    imma::QMeta *qm_qkv = nullptr, *qm_o = nullptr, *qm_gu = nullptr, *qm_d = nullptr;
+    __half *kcache = nullptr, *vcache = nullptr, *x_f16 = nullptr;
+    long long* ids = nullptr;
+    long long* ids_stage = nullptr;
+    int* pos = nullptr;
+    int launches = 0;
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int glue_launch(const onebit_decoder* D, GlueArgs& g, cudaStream_t s) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+    return dispatch_dtype(D->cfg.param_dtype, [&](auto pt) {
+        using TP = decltype(pt);
+        auto kern = glue_kernel<TP>;
+        if (dev >= 0 && dev < 64 && !configured[dev]) {
+            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(glue_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(glue_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(glue_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            configured[dev] = true;
+        }
+        return launch_pdl(kern, dim3(g.M, g.nprob), dim3(kGlueThreads), (size_t)g.K * sizeof(float), s, g);
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+void onebit_decoder_destroy(onebit_decoder* D) {
+    if (!D) return;
+    cudaFree(D->arena);
+    delete D;
+}
+
+int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg, const onebit_layer_params* layers,
+                          const void* embed_tokens_f16, const void* final_norm, const void* lm_head_f16,
+                          const float* rope_cos, const float* rope_sin, onebit_allreduce_fn allreduce,
+                          void* allreduce_user) {
+    ONEBIT_REQUIRE(out && cfg && layers && embed_tokens_f16 && final_norm && lm_head_f16 && rope_cos && rope_sin,
+                   "decoder_create: NULL argument");
+    *out = nullptr;
+    const int H = cfg->hidden_size, I = cfg->intermediate_size, L = cfg->num_layers, B = cfg->max_batch;
+    ONEBIT_REQUIRE(dtype_ok(cfg->param_dtype), "decoder_create: bad param_dtype");
+    ONEBIT_REQUIRE(H > 0 && I > 0 && L > 0 && cfg->num_heads > 0 && cfg->vocab_size > 0 && cfg->max_seq_len > 0,
+                   "decoder_create: bad sizes");
+    ONEBIT_REQUIRE(H == cfg->num_heads * kHeadDim, "decoder_create: only head_dim 128 (LLaMA-7B/13B) is built");
+    ONEBIT_REQUIRE(H % imma::kUnitCols == 0 && I % imma::kUnitCols == 0 && I <= 14336 && H <= 14336,
+                   "decoder_create: hidden/intermediate size must be multiples of 256 and <= 14336");
+    ONEBIT_REQUIRE(B >= 1 && B <= imma::kMaxTokens, "decoder_create: the fused step serves batch 1..8 per replica");
+    ONEBIT_REQUIRE(cfg->tp_size <= 1, "decoder_create: tensor-parallel shards are not wired in this build");
+    ONEBIT_REQUIRE(H % 8 == 0, "decoder_create: hidden must be a multiple of 8");
+    onebit_decoder* D = new (std::nothrow) onebit_decoder();
+    ONEBIT_REQUIRE(D, "decoder_create: out of host memory");
+    D->cfg = *cfg;
+    D->layers.assign(layers, layers + L);
+    D->embed = static_cast<const __half*>(embed_tokens_f16);
+    D->final_norm = final_norm;
+    D->lm_head = static_cast<const __half*>(lm_head_f16);
+    D->rope_cos = rope_cos;
+    D->rope_sin = rope_sin;
+    D->allreduce = allreduce;
+    D->allreduce_user = allreduce_user;
+
+    const int uH = H / imma::kUnitCols, uI = I / imma::kUnitCols;
+    const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_res0 = take((size_t)B * H * 4), o_res1 = take((size_t)B * H * 4);
+    const size_t o_tqkv = take((size_t)3 * B * H * 4), o_to = take((size_t)B * H * 4);
+    const size_t o_tgu = take((size_t)2 * B * I * 4), o_td = take((size_t)B * H * 4);
+    const size_t o_att = take((size_t)B * H * 4), o_log = take((size_t)B * cfg->vocab_size * 4);
+    const size_t o_sqkv = take((size_t)3 * cH * B * 8), o_so = take((size_t)cH * B * 8);
+    const size_t o_sgu = take((size_t)2 * cI * B * 8), o_sd = take((size_t)cH * B * 8);
+    const size_t o_dqkv = take((size_t)3 * B * uH * imma::kUnitBytes), o_do = take((size_t)B * uH * imma::kUnitBytes);
+    const size_t o_dgu = take((size_t)2 * B * uH * imma::kUnitBytes), o_dd = take((size_t)B * uI * imma::kUnitBytes);
+    const size_t o_qqkv = take(3 * B * sizeof(imma::QMeta)), o_qo = take(B * sizeof(imma::QMeta));
+    const size_t o_qgu = take(2 * B * sizeof(imma::QMeta)), o_qd = take(B * sizeof(imma::QMeta));
+    const size_t cache_elems = (size_t)L * B * cfg->num_heads * cfg->max_seq_len * kHeadDim;
+    const size_t o_kc = take(cache_elems * 2), o_vc = take(cache_elems * 2);
+    const size_t o_x16 = take((size_t)B * H * 2), o_ids = take(B * 8), o_ids2 = take(B * 8), o_pos = take(B * 4);
+    cudaError_t e = cudaMalloc(&D->arena, off);
+    if (e != cudaSuccess) {
+        delete D;
+        return fail(ONEBIT_ERR_CUDA, std::string("decoder_create: cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    cudaMemset(D->arena, 0, off);
+    char* a = D->arena;
+    D->resid[0] = (float*)(a + o_res0); D->resid[1] = (float*)(a + o_res1);
+    D->t_qkv = (float*)(a + o_tqkv); D->t_o = (float*)(a + o_to); D->t_gu = (float*)(a + o_tgu); D->t_d = (float*)(a + o_td);
+    D->attn_out = (float*)(a + o_att); D->logits = (float*)(a + o_log);
+    D->st_qkv = (float*)(a + o_sqkv); D->st_o = (float*)(a + o_so); D->st_gu = (float*)(a + o_sgu); D->st_d = (float*)(a + o_sd);
+    D->dg_qkv = (uint8_t*)(a + o_dqkv); D->dg_o = (uint8_t*)(a + o_do); D->dg_gu = (uint8_t*)(a + o_dgu); D->dg_d = (uint8_t*)(a + o_dd);
+    D->qm_qkv = (imma::QMeta*)(a + o_qqkv); D->qm_o = (imma::QMeta*)(a + o_qo);
+    D->qm_gu = (imma::QMeta*)(a + o_qgu); D->qm_d = (imma::QMeta*)(a + o_qd);
+    D->kcache = (__half*)(a + o_kc); D->vcache = (__half*)(a + o_vc); D->x_f16 = (__half*)(a + o_x16);
+    D->ids = (long long*)(a + o_ids); D->ids_stage = (long long*)(a + o_ids2); D->pos = (int*)(a + o_pos);
+    *out = D;
+    return ONEBIT_OK;
+}
+
+int onebit_decoder_reset(onebit_decoder* D, const int64_t* ids_host, const int32_t* pos_host, int batch, void* stream) {
+    ONEBIT_REQUIRE(D && ids_host && pos_host && batch >= 1 && batch <= D->cfg.max_batch, "decoder_reset: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ONEBIT_CUDA_TRY(cudaMemcpyAsync(D->ids, ids_host, (size_t)batch * 8, cudaMemcpyHostToDevice, s));
+    ONEBIT_CUDA_TRY(cudaMemcpyAsync(D->pos, pos_host, (size_t)batch * 4, cudaMemcpyHostToDevice, s));
+    ONEBIT_CUDA_TRY(cudaStreamSynchronize(s));
+    return ONEBIT_OK;
+}
+
+const int64_t* onebit_decoder_next_ids(onebit_decoder* D) { return D ? reinterpret_cast<const int64_t*>(D->ids) : nullptr; }
+const int32_t* onebit_decoder_positions(onebit_decoder* D) { return D ? D->pos : nullptr; }
+int onebit_decoder_kernel_launches_per_step(onebit_decoder* D) { return D ? D->launches : 0; }
+
+int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_dev, float* logits_dev, void* stream) {
+    ONEBIT_REQUIRE(D && batch >= 1 && batch <= D->cfg.max_batch, "decoder_step: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const onebit_decoder_config& C = D->cfg;
+    const int H = C.hidden_size, I = C.intermediate_size, M = batch, pd = C.param_dtype;
+    const int uH = H / imma::kUnitCols, uI = I / imma::kUnitCols;
+    const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
+    const size_t dgH = (size_t)C.max_batch * uH * imma::kUnitBytes;
+    int rc, launches = 0;
+    if (forced_ids_dev) {
+        rc = launch_pdl(copy_ids_kernel, dim3(1), dim3(32), 0, s, reinterpret_cast<const long long*>(forced_ids_dev),
+                        D->ids, M);
+        if (rc) return rc;
+        ++launches;
+    }
+    int cur = 0;  // residual ping-pong index holding the current stream
+    for (int l = 0; l < C.num_layers; ++l) {
+        const onebit_layer_params& P = D->layers[l];
+        // ---- glue 1: (embed | resid + LN(down of previous layer)) -> RMSNorm -> q/k/v digits
+        GlueArgs g = {};
+        g.mode = l == 0 ? GLUE_EMBED_NORM : GLUE_RESID_NORM;
+        g.M = M; g.K = H; g.nprob = 3;
+        g.t_a = D->t_d; g.stats_a = D->st_d; g.ncta_a = cH;
+        g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1];
+        g.embed = D->embed; g.ids = D->ids; g.ln_w = P.input_layernorm;
+        g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
+        g.h[0] = P.q.input_factor; g.h[1] = P.k.input_factor; g.h[2] = P.v.input_factor;
+        for (int i = 0; i < 3; ++i) { g.digits[i] = D->dg_qkv + i * dgH; g.qmeta[i] = D->qm_qkv + i * C.max_batch; }
+        rc = glue_launch(D, g, s); if (rc) return rc; ++launches;
+        cur ^= 1;
+        // ---- GEMV q,k,v
+        imma::Args a = {};
+        a.nprob = 3; a.M = M; a.K = H; a.units = uH;
+        const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
+        for (int i = 0; i < 3; ++i) {
+            a.p[i].w = reinterpret_cast<const uint8_t*>(qkv[i]->weight); a.p[i].g = qkv[i]->weight_scale;
+            a.p[i].digits = D->dg_qkv + i * dgH; a.p[i].qmeta = D->qm_qkv + i * C.max_batch;
+            a.p[i].t = D->t_qkv + (size_t)i * C.max_batch * H; a.p[i].stats = D->st_qkv + (size_t)i * cH * C.max_batch * 2;
+            a.p[i].n_rows = H; a.p[i].ld_t = H;
+        }
+        rc = launch_imma_gemv(a, pd, s); if (rc) return rc; ++launches;
+        // ---- attention
+        AttnArgs at = {};
+        at.t_q = a.p[0].t; at.t_k = a.p[1].t; at.t_v = a.p[2].t;
+        at.stats_q = a.p[0].stats; at.stats_k = a.p[1].stats; at.stats_v = a.p[2].stats; at.ncta = cH;
+        at.M = M; at.H = H; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len; at.pos = D->pos;
+        at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
+        const size_t layer_cache = (size_t)C.max_batch * C.num_heads * C.max_seq_len * kHeadDim;
+        at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
+        at.out = D->attn_out; at.ln_eps = C.ln_eps;
+        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), (size_t)C.max_seq_len * sizeof(float), s, at);
+        if (rc) return rc; ++launches;
+        // ---- glue 2: attention output -> o digits
+        g = {};
+        g.mode = GLUE_PLAIN; g.M = M; g.K = H; g.nprob = 1; g.x_plain = D->attn_out;
+        g.h[0] = P.o.input_factor; g.digits[0] = D->dg_o; g.qmeta[0] = D->qm_o;
+        rc = glue_launch(D, g, s); if (rc) return rc; ++launches;
+        // ---- GEMV o
+        a = {};
+        a.nprob = 1; a.M = M; a.K = H; a.units = uH;
+        a.p[0].w = reinterpret_cast<const uint8_t*>(P.o.weight); a.p[0].g = P.o.weight_scale;
+        a.p[0].digits = D->dg_o; a.p[0].qmeta = D->qm_o; a.p[0].t = D->t_o; a.p[0].stats = D->st_o;
+        a.p[0].n_rows = H; a.p[0].ld_t = H;
+        rc = launch_imma_gemv(a, pd, s); if (rc) return rc; ++launches;
+        // ---- glue 3: resid + LN(o) -> RMSNorm -> gate/up digits
+        g = {};
+        g.mode = GLUE_RESID_NORM; g.M = M; g.K = H; g.nprob = 2;
+        g.t_a = D->t_o; g.stats_a = D->st_o; g.ncta_a = cH;
+        g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = P.post_attention_layernorm;
+        g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
+        g.h[0] = P.gate.input_factor; g.h[1] = P.up.input_factor;
+        for (int i = 0; i < 2; ++i) { g.digits[i] = D->dg_gu + i * dgH; g.qmeta[i] = D->qm_gu + i * C.max_batch; }
+        rc = glue_launch(D, g, s); if (rc) return rc; ++launches;
+        cur ^= 1;
+        // ---- GEMV gate, up
+        a = {};
+        a.nprob = 2; a.M = M; a.K = H; a.units = uH;
+        const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
+        for (int i = 0; i < 2; ++i) {
+            a.p[i].w = reinterpret_cast<const uint8_t*>(gu[i]->weight); a.p[i].g = gu[i]->weight_scale;
+            a.p[i].digits = D->dg_gu + i * dgH; a.p[i].qmeta = D->qm_gu + i * C.max_batch;
+            a.p[i].t = D->t_gu + (size_t)i * C.max_batch * I; a.p[i].stats = D->st_gu + (size_t)i * cI * C.max_batch * 2;
+            a.p[i].n_rows = I; a.p[i].ld_t = I;
+        }
+        rc = launch_imma_gemv(a, pd, s); if (rc) return rc; ++launches;
+        // ---- glue 4: silu(LN(gate)) * LN(up) -> down digits
+        g = {};
+        g.mode = GLUE_SILU_MUL; g.M = M; g.K = I; g.nprob = 1;
+        g.t_a = a.p[0].t; g.stats_a = a.p[0].stats; g.ncta_a = cI;
+        g.t_b = a.p[1].t; g.stats_b = a.p[1].stats; g.ncta_b = cI;
+        g.ln_eps = C.ln_eps;
+        g.h[0] = P.down.input_factor; g.digits[0] = D->dg_d; g.qmeta[0] = D->qm_d;
+        rc = glue_launch(D, g, s); if (rc) return rc; ++launches;
+        // ---- GEMV down
+        a = {};
+        a.nprob = 1; a.M = M; a.K = I; a.units = uI;
+        a.p[0].w = reinterpret_cast<const uint8_t*>(P.down.weight); a.p[0].g = P.down.weight_scale;
+        a.p[0].digits = D->dg_d; a.p[0].qmeta = D->qm_d; a.p[0].t = D->t_d; a.p[0].stats = D->st_d;
+        a.p[0].n_rows = H; a.p[0].ld_t = H;
+        rc = launch_imma_gemv(a, pd, s); if (rc) return rc; ++launches;
+    }
+    // ---- final: resid + LN(down) -> RMSNorm(final) -> fp16 x -> lm_head -> argmax
+    GlueArgs g = {};
+    g.mode = GLUE_RESID_NORM; g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1;
+    g.t_a = D->t_d; g.stats_a = D->st_d; g.ncta_a = cH;
+    g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = D->final_norm;
+    g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps; g.x_f16 = D->x_f16;
+    rc = glue_launch(D, g, s); if (rc) return rc; ++launches;
+    float* logits = logits_dev ? logits_dev : D->logits;
+    if (M <= 2) {
+        rc = launch_pdl(lm_head_kernel<2>, dim3((C.vocab_size + 7) / 8), dim3(256), (size_t)M * H * 2, s, D->lm_head,
+                        (const __half*)D->x_f16, logits, C.vocab_size, H, M);
+    } else {
+        static bool configured[64] = {false};
+        int dev = 0;
+        ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !configured[dev]) {
+            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(lm_head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            configured[dev] = true;
+        }
+        rc = launch_pdl(lm_head_kernel<8>, dim3((C.vocab_size + 7) / 8), dim3(256), (size_t)M * H * 2, s, D->lm_head,
+                        (const __half*)D->x_f16, logits, C.vocab_size, H, M);
+    }
+    if (rc) return rc; ++launches;
+    rc = launch_pdl(argmax_advance_kernel, dim3(M), dim3(1024), 0, s, (const float*)logits, C.vocab_size, D->ids, D->pos);
+    if (rc) return rc; ++launches;
+    D->launches = launches;
+    return ONEBIT_OK;
+}
+
+int onebit_decoder_step_host(onebit_decoder* D, int batch, const int64_t* ids_host, int64_t* next_ids_host, void* stream) {
+    ONEBIT_REQUIRE(D && ids_host && next_ids_host && batch >= 1 && batch <= D->cfg.max_batch, "decoder_step_host: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ONEBIT_CUDA_TRY(cudaMemcpyAsync(D->ids_stage, ids_host, (size_t)batch * 8, cudaMemcpyHostToDevice, s));
+    int rc = onebit_decoder_step(D, batch, reinterpret_cast<const int64_t*>(D->ids_stage), nullptr, stream);
+    if (rc != ONEBIT_OK) return rc;
+    ONEBIT_CUDA_TRY(cudaMemcpyAsync(next_ids_host, D->ids, (size_t)batch * 8, cudaMemcpyDeviceToHost, s));
+    ONEBIT_CUDA_TRY(cudaStreamSynchronize(s));
+    return ONEBIT_OK;
+}
+
+}  // extern "C"

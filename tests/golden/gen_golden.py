@@ -166,9 +166,9 @@ def import_reference_transformers():
     return BitLlamaConfig, BitLlamaForCausalLMInf
 
 
-TINY = dict(vocab_size=384, hidden_size=256, intermediate_size=688, num_hidden_layers=2, num_attention_heads=4,
-            num_key_value_heads=4, max_position_embeddings=256, rms_norm_eps=1e-6, hidden_act="silu",
-            rope_theta=10000.0, pad_token_id=0, bos_token_id=1, eos_token_id=2, tie_word_embeddings=False)
+TINY = dict(vocab_size=384, hidden_size=256, intermediate_size=768, num_hidden_layers=2, num_attention_heads=2,
+            num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-6, hidden_act="silu",
+            rope_theta=10000.0, pad_token_id=0, bos_token_id=1, eos_token_id=None, tie_word_embeddings=False)
 
 
 def gen_model():
