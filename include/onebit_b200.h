@@ -172,6 +172,9 @@ ONEBIT_API int onebit_decoder_step(onebit_decoder* dec, int batch, const int64_t
 /* Host-buffer step for the end-to-end timing: ids from host (pinned), next ids back to host, synchronises. */
 ONEBIT_API int onebit_decoder_step_host(onebit_decoder* dec, int batch, const int64_t* ids_host,
                                         int64_t* next_ids_host, void* stream);
+/* Only the BitLinear GEMV launches of a step (4 per layer) on whatever activation digits are resident — the
+ * weight-streaming kernel chain by itself, used by bench.py for the roofline measurement. */
+ONEBIT_API int onebit_decoder_gemv_only(onebit_decoder* dec, int batch, void* stream);
 ONEBIT_API const int64_t* onebit_decoder_next_ids(onebit_decoder* dec);  /* device int64 [max_batch] */
 ONEBIT_API const int32_t* onebit_decoder_positions(onebit_decoder* dec); /* device int32 [max_batch] */
 ONEBIT_API int onebit_decoder_kernel_launches_per_step(onebit_decoder* dec);

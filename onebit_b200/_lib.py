@@ -8,7 +8,9 @@ import ctypes
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libonebit_b200.so"
+import os as _os
+
+LIB_PATH = PKG / f"libonebit_b200{_os.environ.get('ONEBIT_LIB_SUFFIX', '')}.so"
 
 OK = 0
 F16, BF16, F32 = 0, 1, 2
@@ -42,6 +44,7 @@ SIGNATURES = {
     "onebit_decoder_reset": (_int, [_vp, _vp, _vp, _int, _vp]),
     "onebit_decoder_step": (_int, [_vp, _int, _vp, _vp, _vp]),
     "onebit_decoder_step_host": (_int, [_vp, _int, _vp, _vp, _vp]),
+    "onebit_decoder_gemv_only": (_int, [_vp, _int, _vp]),
     "onebit_decoder_next_ids": (_vp, [_vp]),
     "onebit_decoder_positions": (_vp, [_vp]),
     "onebit_decoder_kernel_launches_per_step": (_int, [_vp]),

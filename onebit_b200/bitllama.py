@@ -152,7 +152,7 @@ class BitLlamaDecoderB200:
         Leaves logits in `self.logits[:batch]` and the next ids on the device (`next_ids()`)."""
         forced = forced_ids is not None
         if forced:
-            self.forced[: self.batch].copy_(forced_ids.reshape(-1).to(self.device, torch.int64), non_blocking=True)
+            self.forced[: self.batch].copy_(forced_ids.reshape(-1), non_blocking=True)  # H2D if the ids are on the host
         with torch.cuda.device(self.device):
             if not self.use_graph:
                 self._enqueue(forced)

@@ -15,8 +15,10 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-LIB = PKG / "libonebit_b200.so"
-OBJ = PKG / "build"
+SUFFIX = os.environ.get("ONEBIT_LIB_SUFFIX", "")          # e.g. "_trace" for an instrumented side build
+EXTRA = os.environ.get("ONEBIT_NVCC_EXTRA", "").split()   # e.g. -DONEBIT_TRACE
+LIB = PKG / f"libonebit_b200{SUFFIX}.so"
+OBJ = PKG / f"build{SUFFIX}"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -41,7 +43,7 @@ def _stale() -> bool:
 def _compile(src: Path, verbose: bool) -> Path:
     obj = OBJ / (src.stem + ".o")
     flags = [f for f in FLAGS if not (src.name in PRECISE and f == "--use_fast_math")]
-    cmd = [NVCC, *ARCH, *flags, "-c", str(src), "-o", str(obj)]
+    cmd = [NVCC, *ARCH, *flags, *EXTRA, "-c", str(src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), flush=True)

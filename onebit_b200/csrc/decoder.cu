@@ -47,99 +47,179 @@ struct GlueArgs {
     __half* x_f16;                                          // optional [M][K] (lm_head input)
 };
 
-__device__ __forceinline__ float block_sum_f(float v, float* sh) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
-    return r;
-}
-
-// mean / rstd of a BitLinear output over its N rows from the GEMV's per-CTA (sum, sum sq) partials.
-__device__ __forceinline__ void ln_stats(const float* stats, int ncta, int M, int m, int n_rows, float eps,
-                                         float* sh2, float& mean, float& rstd) {
-    // warp 0 sums the partials in double (<= a few hundred values), broadcast through shared memory
-    if (threadIdx.x < 32) {
-        double s = 0.0, q = 0.0;
-        for (int c = threadIdx.x; c < ncta; c += 32) {
-            const float2 p = *reinterpret_cast<const float2*>(stats + ((size_t)c * M + m) * 2);
-            s += (double)p.x;
-            q += (double)p.y;
-        }
+// ---- block-wide helpers for the latency-critical single-CTA kernels --------------------------------------
+// All global loads a thread needs are issued up front (one exposed L2 round trip per kernel instead of one per
+// loop iteration); reductions carry up to four values through one shared-memory exchange.
+template <int NVAL>
+__device__ __forceinline__ void block_reduce_sum(double (&v)[NVAL], double* sh /*[32][NVAL] + NVAL*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-        if (threadIdx.x == 0) {
-            const double mu = s / (double)n_rows;
-            const double var = fmax(q / (double)n_rows - mu * mu, 0.0);  // biased variance (nn.LayerNorm)
-            sh2[0] = (float)mu;
-            sh2[1] = (float)(1.0 / sqrt(var + (double)eps));
+    for (int i = 0; i < NVAL; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    __syncthreads();  // protect sh from the previous use
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < NVAL; ++i) sh[warp * NVAL + i] = v[i];
+    __syncthreads();
+    if (warp == 0) {  // second level in one warp (fixed order: deterministic), result broadcast through sh
+#pragma unroll
+        for (int i = 0; i < NVAL; ++i) {
+            double r = lane < nw ? sh[lane * NVAL + i] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (lane == 0) sh[32 * NVAL + i] = r;
         }
     }
     __syncthreads();
-    mean = sh2[0];
-    rstd = sh2[1];
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NVAL; ++i) v[i] = sh[32 * NVAL + i];
+}
+
+template <typename TP>
+__device__ __forceinline__ float4 load_param4(const TP* p, int i4);
+template <>
+__device__ __forceinline__ float4 load_param4<float>(const float* p, int i4) {
+    return reinterpret_cast<const float4*>(p)[i4];
+}
+template <>
+__device__ __forceinline__ float4 load_param4<__half>(const __half* p, int i4) {
+    const uint2 r = reinterpret_cast<const uint2*>(p)[i4];
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <>
+__device__ __forceinline__ float4 load_param4<__nv_bfloat16>(const __nv_bfloat16* p, int i4) {
+    const uint2 r = reinterpret_cast<const uint2*>(p)[i4];
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// (sum, sum of squares) partials of one BitLinear output: this thread's share of the [ncta][M][2] array
+__device__ __forceinline__ void load_stat_partials(const float* stats, int ncta, int M, int m, double& s, double& q) {
+    for (int c = threadIdx.x; c < ncta; c += blockDim.x) {
+        const float2 p = *reinterpret_cast<const float2*>(stats + ((size_t)c * M + m) * 2);
+        s += (double)p.x;
+        q += (double)p.y;
+    }
+}
+__device__ __forceinline__ void finish_ln(double s, double q, int n_rows, float eps, float& mean, float& rstd) {
+    const double mu = s / (double)n_rows;
+    const double var = fmax(q / (double)n_rows - mu * mu, 0.0);  // biased variance (nn.LayerNorm)
+    mean = (float)mu;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 // One CTA per (token, problem): builds x (the BitLinear input) in shared memory, then quantises h_p * x.
-template <typename TP>
-__global__ void __launch_bounds__(kGlueThreads) glue_kernel(const __grid_constant__ GlueArgs A) {
+// NV4 = ceil(K / 4 / kGlueThreads): float4 values each thread keeps in registers.
+template <typename TP, int NV4>
+__global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_constant__ GlueArgs A) {
     extern __shared__ __align__(16) float xs[];  // [K]
-    __shared__ float sh[kGlueThreads / 32];
-    __shared__ float sh2[2];
+    __shared__ double shd[33 * 4];
     __shared__ long long scratch[kGlueThreads / 32];
     imma::pdl_launch_dependents();
     imma::pdl_wait();
-    const int m = blockIdx.x, p = blockIdx.y, K = A.K;
-    const TP* lnw = static_cast<const TP*>(A.ln_w);
-
-    if (A.mode == GLUE_EMBED_NORM || A.mode == GLUE_RESID_NORM) {
-        float mean = 0.f, rstd = 0.f;
-        if (A.mode == GLUE_RESID_NORM) ln_stats(A.stats_a, A.ncta_a, A.M, m, K, A.ln_eps, sh2, mean, rstd);
-        float ss = 0.f;
-        for (int k = threadIdx.x; k < K; k += kGlueThreads) {
-            float r;
-            if (A.mode == GLUE_EMBED_NORM)
-                r = __half2float(A.embed[(size_t)A.ids[m] * K + k]);
-            else
-                r = A.resid_in[(size_t)m * K + k] + (A.t_a[(size_t)m * K + k] - mean) * rstd;  // bitnet.py:118 + :912
-            if (p == 0) A.resid_out[(size_t)m * K + k] = r;
-            xs[k] = r;
-            ss += r * r;
+    const int m = blockIdx.x, p = blockIdx.y, K = A.K, K4 = K >> 2, tid = threadIdx.x;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 va[NV4], vb[NV4], vw[NV4], vh[NV4];
+    const bool need_h = !A.write_x_f16;
+    const bool norm_mode = A.mode == GLUE_EMBED_NORM || A.mode == GLUE_RESID_NORM;
+    // ---- every global load, up front
+    double st[4] = {0.0, 0.0, 0.0, 0.0};
+    if (A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL) load_stat_partials(A.stats_a, A.ncta_a, A.M, m, st[0], st[1]);
+    if (A.mode == GLUE_SILU_MUL) load_stat_partials(A.stats_b, A.ncta_b, A.M, m, st[2], st[3]);
+    const float4* a4 = nullptr;
+    const float4* b4 = nullptr;
+    const __half* erow = nullptr;
+    if (A.mode == GLUE_EMBED_NORM) erow = A.embed + (size_t)A.ids[m] * K;
+    else if (A.mode == GLUE_RESID_NORM) { a4 = reinterpret_cast<const float4*>(A.t_a + (size_t)m * K); b4 = reinterpret_cast<const float4*>(A.resid_in + (size_t)m * K); }
+    else if (A.mode == GLUE_SILU_MUL) { a4 = reinterpret_cast<const float4*>(A.t_a + (size_t)m * K); b4 = reinterpret_cast<const float4*>(A.t_b + (size_t)m * K); }
+    else a4 = reinterpret_cast<const float4*>(A.x_plain + (size_t)m * K);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int i4 = i * kGlueThreads + tid;
+        const bool ok = i4 < K4;
+        va[i] = zero4; vb[i] = zero4; vw[i] = zero4; vh[i] = zero4;
+        if (ok) {
+            if (erow) va[i] = load_param4<__half>(erow, i4);
+            if (a4) va[i] = a4[i4];
+            if (b4) vb[i] = b4[i4];
+            if (norm_mode) vw[i] = load_param4<TP>(static_cast<const TP*>(A.ln_w), i4);
+            if (need_h) vh[i] = load_param4<TP>(static_cast<const TP*>(A.h[p]), i4);
         }
-        const float var = block_sum_f(ss, sh) / (float)K;           // LlamaRMSNorm :77
-        const float rr = rsqrtf(var + A.rms_eps);
-        for (int k = threadIdx.x; k < K; k += kGlueThreads) xs[k] = xs[k] * rr * to_f32(lnw[k]);
-    } else if (A.mode == GLUE_SILU_MUL) {
-        float mean_a, rstd_a, mean_b, rstd_b;
-        ln_stats(A.stats_a, A.ncta_a, A.M, m, K, A.ln_eps, sh2, mean_a, rstd_a);
-        ln_stats(A.stats_b, A.ncta_b, A.M, m, K, A.ln_eps, sh2, mean_b, rstd_b);
-        for (int k = threadIdx.x; k < K; k += kGlueThreads) {
-            const float a = (A.t_a[(size_t)m * K + k] - mean_a) * rstd_a;
-            const float b = (A.t_b[(size_t)m * K + k] - mean_b) * rstd_b;
-            xs[k] = a / (1.f + expf(-a)) * b;  // act_fn(gate) * up, modeling_bitllama.py:257
-        }
-    } else {
-        for (int k = threadIdx.x; k < K; k += kGlueThreads) xs[k] = A.x_plain[(size_t)m * K + k];
     }
-    __syncthreads();
+    // ---- LayerNorm statistics of the producer(s) (bitnet.py:118), from the GEMV's per-CTA partials
+    float mean_a = 0.f, rstd_a = 1.f, mean_b = 0.f, rstd_b = 1.f;
+    if (A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL) {
+        block_reduce_sum<4>(st, shd);
+        finish_ln(st[0], st[1], K, A.ln_eps, mean_a, rstd_a);
+        if (A.mode == GLUE_SILU_MUL) finish_ln(st[2], st[3], K, A.ln_eps, mean_b, rstd_b);
+    }
+    // ---- x
+    if (norm_mode) {
+        double ss[1] = {0.0};
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) {
+            const int i4 = i * kGlueThreads + tid;
+            if (i4 < K4) {
+                float4 r = va[i];
+                if (A.mode == GLUE_RESID_NORM) {  // residual + LayerNorm(o / down output), :912 / :918
+                    r.x = vb[i].x + (va[i].x - mean_a) * rstd_a; r.y = vb[i].y + (va[i].y - mean_a) * rstd_a;
+                    r.z = vb[i].z + (va[i].z - mean_a) * rstd_a; r.w = vb[i].w + (va[i].w - mean_a) * rstd_a;
+                }
+                if (p == 0) reinterpret_cast<float4*>(A.resid_out + (size_t)m * K)[i4] = r;
+                va[i] = r;
+                part += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+            }
+        }
+        ss[0] = (double)part;
+        block_reduce_sum<1>(ss, shd);
+        const float rr = rsqrtf((float)(ss[0] / (double)K) + A.rms_eps);  // LlamaRMSNorm :77-78
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) {
+            va[i].x *= rr * vw[i].x; va[i].y *= rr * vw[i].y; va[i].z *= rr * vw[i].z; va[i].w *= rr * vw[i].w;
+        }
+    } else if (A.mode == GLUE_SILU_MUL) {
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) {
+            const float a[4] = {va[i].x, va[i].y, va[i].z, va[i].w}, b[4] = {vb[i].x, vb[i].y, vb[i].z, vb[i].w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float g = (a[e] - mean_a) * rstd_a, u = (b[e] - mean_b) * rstd_b;
+                o[e] = g / (1.f + expf(-g)) * u;  // act_fn(gate) * up, modeling_bitllama.py:257
+            }
+            va[i] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
     if (A.write_x_f16) {
         if (p == 0)
-            for (int k = threadIdx.x; k < K; k += kGlueThreads) A.x_f16[(size_t)m * K + k] = __float2half_rn(xs[k]);
+#pragma unroll
+            for (int i = 0; i < NV4; ++i) {
+                const int i4 = i * kGlueThreads + tid;
+                if (i4 < K4) {
+                    const __half2 lo = __floats2half2_rn(va[i].x, va[i].y), hi = __floats2half2_rn(va[i].z, va[i].w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    reinterpret_cast<uint2*>(A.x_f16 + (size_t)m * K)[i4] = pk;
+                }
+            }
         return;
     }
-    // x' = h_p * x (bitnet.py:113), amax, digits
-    const TP* h = static_cast<const TP*>(A.h[p]);
+    // ---- x' = h_p * x (bitnet.py:113), amax, digits
     float am = 0.f;
-    for (int k = threadIdx.x; k < K; k += kGlueThreads) {
-        const float v = xs[k] * to_f32(h[k]);
-        xs[k] = v;
-        am = fmaxf(am, fabsf(v));
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int i4 = i * kGlueThreads + tid;
+        if (i4 < K4) {
+            const float4 v = make_float4(va[i].x * vh[i].x, va[i].y * vh[i].y, va[i].z * vh[i].z, va[i].w * vh[i].w);
+            reinterpret_cast<float4*>(xs)[i4] = v;
+            am = fmaxf(am, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
     }
     __syncthreads();
     imma::quantize_from_smem(xs, K, am, A.digits[p] + (size_t)m * (K / imma::kUnitCols) * imma::kUnitBytes,
@@ -161,16 +241,23 @@ struct AttnArgs {
 __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ AttnArgs A) {
     extern __shared__ __align__(16) float sc[];  // [T] scores
     __shared__ float qs[kHeadDim];
-    __shared__ float sh2[2];
+    __shared__ double shd[33 * 6];
     __shared__ float red[kHeadDim / 32];
     imma::pdl_launch_dependents();
     imma::pdl_wait();
     const int m = blockIdx.x, hd = blockIdx.y, d = threadIdx.x, lane = d & 31, warp = d >> 5;
     const int pos = A.pos[m], T = pos + 1;
     float mq, rq, mk, rk, mv, rv;
-    ln_stats(A.stats_q, A.ncta, A.M, m, A.H, A.ln_eps, sh2, mq, rq);
-    ln_stats(A.stats_k, A.ncta, A.M, m, A.H, A.ln_eps, sh2, mk, rk);
-    ln_stats(A.stats_v, A.ncta, A.M, m, A.H, A.ln_eps, sh2, mv, rv);
+    {
+        double st[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        load_stat_partials(A.stats_q, A.ncta, A.M, m, st[0], st[1]);
+        load_stat_partials(A.stats_k, A.ncta, A.M, m, st[2], st[3]);
+        load_stat_partials(A.stats_v, A.ncta, A.M, m, st[4], st[5]);
+        block_reduce_sum<6>(st, shd);
+        finish_ln(st[0], st[1], A.H, A.ln_eps, mq, rq);
+        finish_ln(st[2], st[3], A.H, A.ln_eps, mk, rk);
+        finish_ln(st[4], st[5], A.H, A.ln_eps, mv, rv);
+    }
     const size_t col = (size_t)m * A.H + hd * kHeadDim;
     const int half = kHeadDim / 2, dp = d < half ? d + half : d - half, fi = d < half ? d : d - half;
     const float c = A.rope_cos[(size_t)pos * half + fi], s = A.rope_sin[(size_t)pos * half + fi];
@@ -348,20 +435,27 @@ namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int glue_launch(const onebit_decoder* D, GlueArgs& g, cudaStream_t s) {
+template <typename TP, int NV4>
+int glue_launch_inst(GlueArgs& g, cudaStream_t s) {
+    auto kern = glue_kernel<TP, NV4>;
     static bool configured[64] = {false};
     int dev = 0;
     ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        configured[dev] = true;
+    }
+    return launch_pdl(kern, dim3(g.M, g.nprob), dim3(kGlueThreads), (size_t)g.K * sizeof(float), s, g);
+}
+
+int glue_launch(const onebit_decoder* D, GlueArgs& g, cudaStream_t s) {
+    const int nv4 = (g.K / 4 + kGlueThreads - 1) / kGlueThreads;
     return dispatch_dtype(D->cfg.param_dtype, [&](auto pt) {
         using TP = decltype(pt);
-        auto kern = glue_kernel<TP>;
-        if (dev >= 0 && dev < 64 && !configured[dev]) {
-            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(glue_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(glue_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(glue_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            configured[dev] = true;
-        }
-        return launch_pdl(kern, dim3(g.M, g.nprob), dim3(kGlueThreads), (size_t)g.K * sizeof(float), s, g);
+        if (nv4 <= 2) return glue_launch_inst<TP, 2>(g, s);
+        if (nv4 <= 3) return glue_launch_inst<TP, 3>(g, s);
+        if (nv4 <= 6) return glue_launch_inst<TP, 6>(g, s);
+        return glue_launch_inst<TP, 7>(g, s);
     });
 }
 
@@ -581,6 +675,54 @@ int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_
     rc = launch_pdl(argmax_advance_kernel, dim3(M), dim3(1024), 0, s, (const float*)logits, C.vocab_size, D->ids, D->pos);
     if (rc) return rc; ++launches;
     D->launches = launches;
+    return ONEBIT_OK;
+}
+
+// Enqueue only the BitLinear GEMV launches of one step (4 per layer), reusing whatever activation digits are
+// resident: the weight-streaming kernel chain on its own, for the roofline measurement in bench.py.
+int onebit_decoder_gemv_only(onebit_decoder* D, int batch, void* stream) {
+    ONEBIT_REQUIRE(D && batch >= 1 && batch <= D->cfg.max_batch, "decoder_gemv_only: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const onebit_decoder_config& C = D->cfg;
+    const int H = C.hidden_size, I = C.intermediate_size, M = batch, pd = C.param_dtype;
+    const int uH = H / imma::kUnitCols, uI = I / imma::kUnitCols;
+    const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
+    const size_t dgH = (size_t)C.max_batch * uH * imma::kUnitBytes;
+    for (int l = 0; l < C.num_layers; ++l) {
+        const onebit_layer_params& P = D->layers[l];
+        imma::Args a = {};
+        a.nprob = 3; a.M = M; a.K = H; a.units = uH;
+        const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
+        for (int i = 0; i < 3; ++i) {
+            a.p[i].w = reinterpret_cast<const uint8_t*>(qkv[i]->weight); a.p[i].g = qkv[i]->weight_scale;
+            a.p[i].digits = D->dg_qkv + i * dgH; a.p[i].qmeta = D->qm_qkv + i * C.max_batch;
+            a.p[i].t = D->t_qkv + (size_t)i * C.max_batch * H; a.p[i].stats = D->st_qkv + (size_t)i * cH * C.max_batch * 2;
+            a.p[i].n_rows = H; a.p[i].ld_t = H;
+        }
+        int rc = launch_imma_gemv(a, pd, s); if (rc) return rc;
+        a = {};
+        a.nprob = 1; a.M = M; a.K = H; a.units = uH;
+        a.p[0].w = reinterpret_cast<const uint8_t*>(P.o.weight); a.p[0].g = P.o.weight_scale;
+        a.p[0].digits = D->dg_o; a.p[0].qmeta = D->qm_o; a.p[0].t = D->t_o; a.p[0].stats = D->st_o;
+        a.p[0].n_rows = H; a.p[0].ld_t = H;
+        rc = launch_imma_gemv(a, pd, s); if (rc) return rc;
+        a = {};
+        a.nprob = 2; a.M = M; a.K = H; a.units = uH;
+        const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
+        for (int i = 0; i < 2; ++i) {
+            a.p[i].w = reinterpret_cast<const uint8_t*>(gu[i]->weight); a.p[i].g = gu[i]->weight_scale;
+            a.p[i].digits = D->dg_gu + i * dgH; a.p[i].qmeta = D->qm_gu + i * C.max_batch;
+            a.p[i].t = D->t_gu + (size_t)i * C.max_batch * I; a.p[i].stats = D->st_gu + (size_t)i * cI * C.max_batch * 2;
+            a.p[i].n_rows = I; a.p[i].ld_t = I;
+        }
+        rc = launch_imma_gemv(a, pd, s); if (rc) return rc;
+        a = {};
+        a.nprob = 1; a.M = M; a.K = I; a.units = uI;
+        a.p[0].w = reinterpret_cast<const uint8_t*>(P.down.weight); a.p[0].g = P.down.weight_scale;
+        a.p[0].digits = D->dg_d; a.p[0].qmeta = D->qm_d; a.p[0].t = D->t_d; a.p[0].stats = D->st_d;
+        a.p[0].n_rows = H; a.p[0].ld_t = H;
+        rc = launch_imma_gemv(a, pd, s); if (rc) return rc;
+    }
     return ONEBIT_OK;
 }
 

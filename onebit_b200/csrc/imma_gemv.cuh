@@ -35,6 +35,13 @@
 namespace onebit {
 namespace imma {
 
+#ifdef ONEBIT_TRACE
+__device__ long long g_trace[8];
+#define TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_trace[i] = clock64(); } while (0)
+#else
+#define TR(i)
+#endif
+
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kRows = 32;           // rows per CTA
@@ -121,7 +128,7 @@ inline size_t gemv_smem_bytes(int M, int units, int NT) {
 
 // UPW = ceil(units / kWarps) compile-time bound of the weight-word register file (2, 3, 6 or 7).
 template <typename TP, int NT, int UPW>
-__global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const __grid_constant__ Args A) {
+__global__ void __launch_bounds__(kThreads, (NT == 1 && UPW <= 3) ? 5 : 2) gemv_kernel(const __grid_constant__ Args A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;
     const int M = A.M;
@@ -139,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const __grid_constant
     const int row0 = cta * kRows;
     const int Kb = A.K >> 3;
 
+    TR(0);
     // ---- 1. every weight word of this warp goes in flight (touches only static data) ----
     uint2 wreg[UPW][4];
     {
@@ -158,8 +166,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const __grid_constant
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // epilogue operands: this thread finalises (row = tid & 31, token = tid >> 5); g is static -> load it now
+    const int er = tid & 31, em = tid >> 5;
+    float gval = 1.f;
+    if (P.g != nullptr && row0 + er < P.n_rows) gval = to_f32(static_cast<const TP*>(P.g)[row0 + er]);
+    TR(1);
     pdl_launch_dependents();
     pdl_wait();  // producer's digits / qmeta are now visible
+    TR(2);
+    QMeta qm;
+    qm.inv_scale = 0.0;
+    qm.qtot = 0;
+    if (em < M) qm = P.qmeta[em];
 
     // ---- 2. activation digits: one bulk copy into shared memory ----
     const uint32_t dbytes = (uint32_t)M * A.units * kUnitBytes;
@@ -169,14 +187,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const __grid_constant
     }
     __syncthreads();  // barrier init visible to all waiters
     mbar_wait(&s_bar, 0);
+    TR(3);
 
-    int acc[2][NT][4];
+    // two independent accumulator sets per row tile (even / odd plane pairs) halve the IMMA dependency chains
+    int acc2[2][2][NT][4];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int z = 0; z < 2; ++z)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[r][nt][i] = 0;
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc2[z][r][nt][i] = 0;
 
     // ---- 3. main loop: 4 LOP3 + 1 IMMA per (16 rows x 32 columns x plane) ----
 #pragma unroll
@@ -203,12 +225,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const __grid_constant
                         const uint32_t a2 = plane(wreg[s][2 * r].y, mask), a3 = plane(wreg[s][2 * r + 1].y, mask);
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt)
-                            imma16832(acc[r][nt], a0, a1, a2, a3, jj ? bv[nt].z : bv[nt].x, jj ? bv[nt].w : bv[nt].y);
+                            imma16832(acc2[jp & 1][r][nt], a0, a1, a2, a3, jj ? bv[nt].z : bv[nt].x,
+                                      jj ? bv[nt].w : bv[nt].y);
                     }
                 }
             }
         }
     }
+
+    TR(4);
+    int acc[2][NT][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[r][nt][i] = acc2[0][r][nt][i] + acc2[1][r][nt][i];
 
     // ---- 4. combine the K split across warps, undo the quantisation, scale, store ----
     constexpr int kCols = 8 * NT;
@@ -232,10 +264,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const __grid_constant
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
         const long long V = (((long long)a.w * 256 + a.z) * 256 + a.y) * 256 + a.x;  // = 128 * sum_{bit=1} q
-        const QMeta qm = P.qmeta[m];
         float val = (float)((double)(qm.qtot - 2 * (V >> 7)) * qm.inv_scale);
         if (n < P.n_rows) {
-            if (P.g != nullptr) val *= to_f32(static_cast<const TP*>(P.g)[n]);
+            val *= gval;
             P.t[(size_t)m * P.ld_t + n] = val;
             su = val;
             sq = val * val;
@@ -246,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const __grid_constant
         sq = warp_sum(sq);
         if (lane == 0 && m < M) *reinterpret_cast<float2*>(P.stats + ((size_t)cta * M + m) * 2) = make_float2(su, sq);
     }
+    TR(5);
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -165,3 +165,13 @@ int launch_matvec_mma(const void* x, const int8_t* w, const void* g, const void*
 }
 
 }  // namespace onebit
+
+// Debug only (side builds with -DONEBIT_TRACE): clock64() stamps of CTA 0 / thread 0 of the last GEMV launch.
+extern "C" __attribute__((visibility("default"))) int onebit_debug_read_trace(long long* out8) {
+#ifdef ONEBIT_TRACE
+    return cudaMemcpyFromSymbol(out8, onebit::imma::g_trace, sizeof(long long) * 8) == cudaSuccess ? 0 : -2;
+#else
+    (void)out8;
+    return -1;
+#endif
+}
