@@ -132,9 +132,7 @@ def run_reference(args, rank: int):
     name, cfg = model_config(args.model)
     res = None
     t_all = time.perf_counter()
-    for _ in range(max(1, args.warmup) - 1 + 1):  # bounded: each "step" is one sample of the layer-level workload
-        pass
-    vals = []
+    vals = []  # each "step" is one bounded sample of the layer-level workload (the sampler warms itself up)
     for _ in range(max(1, args.steps)):
         res = cpu_decode_baseline(cfg, args.batch, tokens=2)
         vals.append(res["value"])
@@ -180,12 +178,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from onebit_b200 import replicas
+
     def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return replicas.max_over_ranks(ms, device=dev)
 
     def prefill():
         dec.reset(prompt[:, 0])
