@@ -52,8 +52,10 @@ static int check_forward_args(const void* x, const int8_t* w, const void* g, con
 
 static int pick_variant(int variant, int64_t m, int64_t k, int64_t n, int act_dtype, int* chosen) {
     switch (variant) {
-        case ONEBIT_VARIANT_AUTO:
-            *chosen = matvec_mma_supported(m, k, n, act_dtype) ? ONEBIT_VARIANT_MMA : ONEBIT_VARIANT_SIMT;
+        case ONEBIT_VARIANT_AUTO:  // decode-size batches: bit-plane IMMA GEMV; larger: tcgen05; odd shapes: CUDA cores
+            *chosen = matvec_mma_supported(m, k, n, act_dtype)
+                          ? ONEBIT_VARIANT_MMA
+                          : (m > 8 && prefill_tc5_supported(m, k, n) ? ONEBIT_VARIANT_TC5 : ONEBIT_VARIANT_SIMT);
             return ONEBIT_OK;
         case ONEBIT_VARIANT_SIMT:
             *chosen = variant;
@@ -64,7 +66,9 @@ static int pick_variant(int variant, int64_t m, int64_t k, int64_t n, int act_dt
             *chosen = variant;
             return ONEBIT_OK;
         case ONEBIT_VARIANT_TC5:
-            return fail(ONEBIT_ERR_INVALID_ARGUMENT, "ONEBIT_VARIANT_TC5 is not built in this version");
+            ONEBIT_REQUIRE(prefill_tc5_supported(m, k, n), "ONEBIT_VARIANT_TC5 does not support this shape (needs K % 64 == 0)");
+            *chosen = variant;
+            return ONEBIT_OK;
         default:
             return fail(ONEBIT_ERR_INVALID_ARGUMENT, "unknown variant code " + std::to_string(variant));
     }
@@ -80,6 +84,11 @@ static int matvec_impl(const void* x, const int8_t* w, const void* g, const void
         if (m > 0 && (!ws || !aligned16(ws) || ws_bytes < matvec_mma_workspace_bytes(m, k)))
             return fail(ONEBIT_ERR_WORKSPACE, "workspace missing, misaligned or smaller than onebit_matvec_workspace_bytes");
         return launch_matvec_mma(x, w, g, h, t, m, k, n, act_dtype, param_dtype, scale_by_g, ws, s);
+    }
+    if (chosen == ONEBIT_VARIANT_TC5) {
+        if (m > 0 && (!ws || !aligned16(ws) || ws_bytes < prefill_tc5_workspace_bytes(m, k, act_dtype, param_dtype)))
+            return fail(ONEBIT_ERR_WORKSPACE, "workspace missing, misaligned or smaller than onebit_matvec_workspace_bytes");
+        return launch_prefill_tc5(x, w, g, h, t, m, k, n, act_dtype, param_dtype, scale_by_g, ws, s);
     }
     return launch_matvec_simt(x, w, g, h, t, m, k, n, act_dtype, param_dtype, scale_by_g, s);
 }
@@ -127,7 +136,10 @@ static size_t t_bytes(int64_t m, int64_t n) {  // t = S @ (h*x) in fp32, before 
 
 size_t onebit_matvec_workspace_bytes(int64_t m, int64_t k) {
     if (m <= 0 || k <= 0) return 16;
-    return matvec_mma_workspace_bytes(m, k);
+    // digits of the IMMA variant (small m) or the fp16 staging of x / h of the tcgen05 variant (fp32 worst case)
+    const size_t a = m <= 8 ? matvec_mma_workspace_bytes(m, k) : 0;
+    const size_t b = prefill_tc5_workspace_bytes(m, k, ONEBIT_F32, ONEBIT_F32);
+    return a > b ? a : b;
 }
 
 size_t onebit_bitlinear_workspace_bytes(int64_t m, int64_t k, int64_t n) {

@@ -79,6 +79,10 @@ size_t matvec_mma_workspace_bytes(int64_t m, int64_t k);
 int launch_matvec_mma(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m,
                       int64_t k, int64_t n, int act_dtype, int param_dtype, bool scale_by_g, void* workspace,
                       cudaStream_t s);
+bool prefill_tc5_supported(int64_t m, int64_t k, int64_t n);
+size_t prefill_tc5_workspace_bytes(int64_t m, int64_t k, int act_dtype, int param_dtype);
+int launch_prefill_tc5(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m, int64_t k,
+                       int64_t n, int act_dtype, int param_dtype, bool scale_by_g, void* workspace, cudaStream_t s);
 int launch_quantize_tokens(const void* x, const void* h, uint8_t* digits, void* qmeta, int64_t m, int64_t k,
                            int act_dtype, int param_dtype, cudaStream_t s);
 

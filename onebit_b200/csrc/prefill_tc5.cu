@@ -1,0 +1,336 @@
+// Large-batch (prefill) variant of the 1-bit linear layer on the 5th-generation tensor cores:
+//     t[m][n] = g[n] * sum_k s(n,k) * h[k] * x[m][k]                      (bitnet.py:113-116)
+// computed as D[n][m] = A[n][:] . B[m][:] with tcgen05.mma (kind::f16, fp32 accumulators in TMEM):
+//   A (M side, 2 x 128 rows per CTA) = the sign matrix with h folded in: A[n][k] = bit ? -h[k] : h[k], built in
+//       registers straight from the 1-bit layout and written once per K chunk to shared memory in the UMMA
+//       SWIZZLE_128B K-major layout. Sign application costs ~1.1 op/weight and needs no shift:
+//       (byte * (0x40008000 >> 2i)) & 0x80008000 puts bits 2i / 2i+1 of a weight byte on the sign positions
+//       of an fp16 pair, and the same LOP3 XORs them onto the (h[k], h[k+1]) pair.
+//   B (N side, 256 tokens per CTA) = x itself (fp16), TMA-loaded (cp.async.bulk.tensor, 128B swizzle), K-major as
+//       stored. h is folded into A, so x needs no pre-multiplication pass and h*x is formed exactly (fp16 x fp16
+//       products are exact in the fp32 accumulator).
+// One expanded weight tile (256 x 64 fp16 = 32 KB from 2 KB of packed bits) is reused across the 256 tokens of
+// the CTA, so the expansion (the reason tcgen05 is NOT used for decode, see imma_gemv.cuh) is amortised:
+// 2 x 4 MMAs of 128x256x16 per chunk = 1024 tensor cycles vs ~170 ALU instructions per expander thread.
+// B traffic: 32 KB per 1024 cycles per SM = 4.7 KB/clk chip-wide, under the ~6.3 KB/clk L2 limit (a 128-row CTA
+// tile would need 9.5 KB/clk).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2-5 = sign expanders, then epilogue (tcgen05.ld -> * g -> coalesced fp32 stores).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace onebit {
+namespace {
+
+constexpr int kTileN = 256;     // weight rows per CTA (two UMMA M=128 tiles)
+constexpr int kTileM = 256;     // tokens per CTA (UMMA N)
+constexpr int kChunkK = 64;     // K columns per pipeline stage (= one 128-byte swizzle row of fp16)
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+constexpr int kABytes = kTileN * kChunkK * 2;  // 32 KB
+constexpr int kBBytes = kTileM * kChunkK * 2;  // 32 KB
+constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024;  // + alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start >> 4 | LBO (unused for one swizzle atom along K) |
+// SBO = 1024 B between 8-row groups | version 1 (sm_100) | layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct PrefillArgs {
+    const uint8_t* w;   // [N][K/8]
+    const __half* h;    // [K] fp16
+    const void* g;      // [N] TP or nullptr
+    float* t;           // [M][N] fp32
+    int M, N, K;
+};
+
+template <typename TP>
+__global__ void __launch_bounds__(kThreads, 1)
+prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ PrefillArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sA = smem;                          // [stage][256 rows][128 B] swizzled
+    unsigned char* sB = smem + kStages * kABytes;      // [stage][256 rows][128 B] swizzled (TMA)
+    __shared__ __align__(8) uint64_t full_a[kStages], full_b[kStages], empty[kStages], tmem_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kTileN, m0 = blockIdx.y * kTileM;
+    const int nchunks = A.K / kChunkK;
+    const int m_valid = min(kTileM, A.M - m0);
+    const int umma_n = max(16, (m_valid + 15) & ~15);  // tokens covered by the MMA (multiple of 16)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_a[s], 128);
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    }
+    if (warp == 1) {  // TMEM: 512 columns (two 128 x 256 fp32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer: x tile [256 tokens][64 k] per stage =====
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kStages, it = c / kStages;
+                if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+                mbar_expect_tx(&full_b[s], kBBytes);
+                tma_load_2d(sB + s * kBBytes, &xmap, c * kChunkK, m0, &full_b[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, umma_n);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kStages, ph = (c / kStages) & 1;
+                mbar_wait(&full_a[s], ph);
+                mbar_wait(&full_b[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(sA + s * kABytes), b_addr = smem_u32(sB + s * kBBytes);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int k = 0; k < kChunkK / 16; ++k) {
+                        const uint64_t ad = umma_desc_sw128(a_addr + half * (128 * 128) + k * 32);
+                        const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
+                        umma_f16(tmem_base + half * 256, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+            }
+            umma_commit(&tmem_full);
+        }
+    } else {
+        // ===== sign expanders: thread e (0..127) owns rows e and e + 128 of the CTA's weight tile =====
+        const int e = threadIdx.x - 64;
+        const int Kb = A.K >> 3;
+        const uint8_t* wrow0 = A.w + (size_t)min(n0 + e, A.N - 1) * Kb;
+        const uint8_t* wrow1 = A.w + (size_t)min(n0 + e + 128, A.N - 1) * Kb;
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % kStages, it = c / kStages;
+            const uint2 w0 = *reinterpret_cast<const uint2*>(wrow0 + c * 8);
+            const uint2 w1 = *reinterpret_cast<const uint2*>(wrow1 + c * 8);
+            const uint4* hp = reinterpret_cast<const uint4*>(A.h + c * kChunkK);  // 8 x 16 B, same for every row
+            if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+            unsigned char* base = sA + s * kABytes;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint2 w = half ? w1 : w0;
+                const int r = e + half * 128;
+                unsigned char* rowp = base + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {  // 16-byte chunk q = columns 8q .. 8q+7 = byte q of the 64-bit word
+                    const uint4 hv = __ldg(hp + q);
+                    // byte q of the row chunk: bit i = column 8q + i. An 8-bit value times (0x40008000 >> 2i) is two
+                    // disjoint shifted copies (no carries): bit 2i lands on bit 15, bit 2i+1 on bit 31.
+                    const uint32_t b8 = __byte_perm(q < 4 ? w.x : w.y, 0u, 0x4440u | (uint32_t)(q & 3));
+                    uint4 o;
+                    o.x = ((b8 * 0x40008000u) & 0x80008000u) ^ hv.x;
+                    o.y = ((b8 * 0x10002000u) & 0x80008000u) ^ hv.y;
+                    o.z = ((b8 * 0x04000800u) & 0x80008000u) ^ hv.z;
+                    o.w = ((b8 * 0x01000200u) & 0x80008000u) ^ hv.w;
+                    *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) << 4)) = o;  // SWIZZLE_128B: chunk ^= row % 8
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+            mbar_arrive(&full_a[s]);
+        }
+        // ===== epilogue: TMEM -> registers -> * g -> t[m][n] (lanes = consecutive n: coalesced) =====
+        mbar_wait(&tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int n = n0 + half * 128 + quarter * 32 + lane;
+            const float gs = (A.g != nullptr && n < A.N) ? to_f32(static_cast<const TP*>(A.g)[n]) : 1.f;
+#pragma unroll 1
+            for (int cb = 0; cb < umma_n; cb += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 256 + cb);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+                    "%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (n < A.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int m = m0 + cb + j;
+                        if (m < A.M) A.t[(size_t)m * A.N + n] = __uint_as_float(v[j]) * gs;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// x (bf16 / fp32) -> fp16 scratch, so that the TMA / MMA B operand is always fp16
+template <typename TX>
+__global__ void to_half_kernel(const TX* __restrict__ x, __half* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2half_rn(to_f32(x[i]));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+bool prefill_tc5_supported(int64_t m, int64_t k, int64_t n) {
+    return m >= 1 && k % kChunkK == 0 && k >= kChunkK && n >= 1 && m < (1ll << 31) && n < (1ll << 31);
+}
+
+size_t prefill_tc5_workspace_bytes(int64_t m, int64_t k, int act_dtype, int param_dtype) {
+    size_t b = 0;
+    if (act_dtype != ONEBIT_F16) b += (((size_t)m * k * 2) + 255) & ~(size_t)255;
+    if (param_dtype != ONEBIT_F16) b += (((size_t)k * 2) + 255) & ~(size_t)255;
+    return b + 256;
+}
+
+int launch_prefill_tc5(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m, int64_t k,
+                       int64_t n, int act_dtype, int param_dtype, bool scale_by_g, void* workspace, cudaStream_t s) {
+    ONEBIT_REQUIRE(prefill_tc5_supported(m, k, n), "prefill_tc5: needs K % 64 == 0");
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return fail(ONEBIT_ERR_CUDA, "prefill_tc5: cuTensorMapEncodeTiled entry point not available");
+    char* ws = static_cast<char*>(workspace);
+    const __half* x16 = static_cast<const __half*>(x);
+    if (act_dtype != ONEBIT_F16) {
+        __half* buf = reinterpret_cast<__half*>(ws);
+        ws += (((size_t)m * k * 2) + 255) & ~(size_t)255;
+        const int64_t total = m * k;
+        const unsigned grid = (unsigned)((total + 255) / 256);
+        if (act_dtype == ONEBIT_BF16)
+            to_half_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), buf, total);
+        else
+            to_half_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), buf, total);
+        ONEBIT_CUDA_TRY(cudaGetLastError());
+        x16 = buf;
+    }
+    const __half* h16 = static_cast<const __half*>(h);
+    if (param_dtype != ONEBIT_F16) {
+        __half* buf = reinterpret_cast<__half*>(ws);
+        const unsigned grid = (unsigned)((k + 255) / 256);
+        if (param_dtype == ONEBIT_BF16)
+            to_half_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(h), buf, k);
+        else
+            to_half_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(h), buf, k);
+        ONEBIT_CUDA_TRY(cudaGetLastError());
+        h16 = buf;
+    }
+    CUtensorMap xmap;
+    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)m};
+    const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)kTileM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(x16), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(ONEBIT_ERR_CUDA, "prefill_tc5: cuTensorMapEncodeTiled failed, code " + std::to_string((int)cr));
+    PrefillArgs a;
+    a.w = reinterpret_cast<const uint8_t*>(w);
+    a.h = h16;
+    a.g = scale_by_g ? g : nullptr;
+    a.t = t;
+    a.M = (int)m;
+    a.N = (int)n;
+    a.K = (int)k;
+    dim3 grid((unsigned)((n + kTileN - 1) / kTileN), (unsigned)((m + kTileM - 1) / kTileM));
+    ONEBIT_REQUIRE(grid.y <= 65535, "prefill_tc5: M too large (max 16.7M tokens)");
+    return dispatch_dtype(param_dtype, [&](auto pt) {
+        using TP = decltype(pt);
+        auto kern = prefill_tc5_kernel<TP>;
+        static bool configured[64] = {false};
+        int dev = 0;
+        ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !configured[dev]) {
+            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            configured[dev] = true;
+        }
+        kern<<<grid, kThreads, kSmemBytes, s>>>(xmap, a);
+        ONEBIT_CUDA_TRY(cudaGetLastError());
+        return ONEBIT_OK;
+    });
+}
+
+}  // namespace onebit

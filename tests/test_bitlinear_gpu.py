@@ -41,6 +41,11 @@ def variants_for(m, k, n, dtype=torch.float16):
     torch.cuda.synchronize()
     if rc == 0:
         out.append("mma")
+    rc = lib.onebit_bitlinear_matvec(x.data_ptr(), w.data_ptr(), g.data_ptr(), g.data_ptr(), t.data_ptr(), m, k, n,
+                                     code, code, 0, ws.data_ptr(), wsb, _lib.VARIANT_TC5, None)
+    torch.cuda.synchronize()
+    if rc == 0:
+        out.append("tc5")
     return out
 
 
@@ -364,3 +369,47 @@ def test_tensor_parallel_halves_compose_to_the_full_layer():
                                              t["h"][r * ks:(r + 1) * ks].contiguous(), scale_by_g=False)
     y = onebit_b200.scale_layernorm(tsum, t["g"], None, torch.float16)
     assert oracle.rel_l2(y.float().cpu().numpy(), want) < REL_TOL
+
+
+@pytest.mark.parametrize("m", [9, 16, 100, 256, 257, 600])
+def test_prefill_tcgen05_variant_against_oracle(m):
+    # tcgen05 / TMEM path: token tails (m % 256, m % 16), weight-row tails (N % 256), several K
+    for (k, n) in [(4096, 4096), (11008, 4096), (1024, 300), (64, 256)]:
+        if m > 300 and k * n > 1024 * 1024:
+            continue  # keep the CPU oracle to a few seconds
+        case = oracle.synth_case(2000 + m, k, n, m)
+        want = oracle.bitlinear_forward_c(case["x"], case["packed"], case["g"], case["h"])
+        got = run(case, "f16", "tc5")
+        r = oracle.rel_l2(got, want)
+        assert r < REL_TOL, (m, k, n, r)
+
+
+def test_prefill_tcgen05_pre_layernorm_and_dtypes():
+    case = oracle.synth_case(2100, 2048, 512, 130, with_bias=True)
+    _, want_u = oracle.bitlinear_forward_c(case["x"], case["packed"], case["g"], case["h"], case["bias"], return_pre_ln=True)
+    d = dev()
+    t = onebit_b200.bitlinear_matvec(torch.from_numpy(case["x"]).to(d, torch.float16), torch.from_numpy(case["packed"]).to(d),
+                                     torch.from_numpy(case["g"]).to(d, torch.float16),
+                                     torch.from_numpy(case["h"]).to(d, torch.float16), scale_by_g=True, variant="tc5")
+    assert oracle.rel_l2(t.cpu().numpy(), want_u) < 1e-5  # fp16 x fp16 products are exact in the fp32 accumulator
+    want = oracle.bitlinear_forward_c(case["x"], case["packed"], case["g"], case["h"], case["bias"])
+    for act in ("bf16", "f32"):
+        c2 = dict(case)
+        if act == "bf16":
+            for key in ("x", "g", "h", "bias"):
+                c2[key] = torch.from_numpy(case[key]).bfloat16().float().numpy()
+            w2 = oracle.bitlinear_forward_c(c2["x"], c2["packed"], c2["g"], c2["h"], c2["bias"])
+        else:
+            w2 = want
+        got = run(c2, act, "tc5")
+        assert oracle.rel_l2(got, w2) < OUT_TOL[act], act
+
+
+def test_auto_dispatch_picks_a_tensor_core_variant_for_every_llama_batch():
+    # AUTO must agree with the forced variants (decode: IMMA, prefill: tcgen05) on the same inputs
+    case = oracle.synth_case(2200, 4096, 4096, 40)
+    a = run(case, "f16", "auto")
+    b = run(case, "f16", "tc5")
+    assert np.array_equal(a, b)
+    case = oracle.synth_case(2201, 4096, 4096, 2)
+    assert np.array_equal(run(case, "f16", "auto"), run(case, "f16", "mma"))
