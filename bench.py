@@ -248,6 +248,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     barrier()
     gemv_ms = e4.elapsed_time(e5) / reps
     clocks = sampler.stop() if sampler else None
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
     if rank != 0:
         return
@@ -263,12 +266,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     tpath = ROOT / "profiles" / "r01_gemv_traffic.json"
     if tpath.exists():
         traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "imma::gemv_kernel (bit-plane IMMA packed-sign GEMV)", "achieved": achieved,
+    fused_on = os.environ.get("ONEBIT_FUSED", "1") != "0"
+    kname = ("fused::fused_gemv_kernel (glue prologue + bit-plane IMMA packed-sign GEMV, one launch per BitLinear group)"
+             if fused_on else "imma::gemv_kernel (bit-plane IMMA packed-sign GEMV)")
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "us_per_launch": gemv_ms * 1e3 / launches,
                 "launches_timed": launches * reps,
-                "how": "CUDA events around 20 replays of a graph holding the step's 4xL GEMV launches (PDL chained), "
-                       "distinct weights per launch (810 MB per replay > L2)",
+                "how": "CUDA events around 20 replays of a graph holding the step's 4xL BitLinear-stage launches (PDL "
+                       "chained, attention / lm_head left out), distinct weights per launch (810 MB per replay > L2)",
                 "step_level": {"bitlinear_GBs_over_whole_step": bb["per_step"] / (ms / K * 1e-3) / 1e9,
                                "frac": bb["per_step"] / (ms / K * 1e-3) / 1e9 / peak}}
     cpu = cpu_decode_baseline(cfg, B, tokens=3) if world == 1 else None

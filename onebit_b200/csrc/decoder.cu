@@ -12,9 +12,11 @@
 // All state that changes between steps (token ids, positions) lives in device memory, so a step is one
 // CUDA graph replay. The residual stream is kept in fp32.
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
+#include "fused_gemv.cuh"
 #include "imma_gemv.cuh"
 
 namespace onebit {
@@ -123,13 +125,13 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
     imma::pdl_wait();
     const int m = blockIdx.x, p = blockIdx.y, K = A.K, K4 = K >> 2, tid = threadIdx.x;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 va[NV4], vb[NV4], vw[NV4], vh[NV4];
+    float4 va[NV4], vb[NV4];
+    fused::Raw4<TP> vw[NV4], vh[NV4];
+    fused::Raw4<__half> ve[NV4];
     const bool need_h = !A.write_x_f16;
     const bool norm_mode = A.mode == GLUE_EMBED_NORM || A.mode == GLUE_RESID_NORM;
     // ---- every global load, up front
     double st[4] = {0.0, 0.0, 0.0, 0.0};
-    if (A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL) load_stat_partials(A.stats_a, A.ncta_a, A.M, m, st[0], st[1]);
-    if (A.mode == GLUE_SILU_MUL) load_stat_partials(A.stats_b, A.ncta_b, A.M, m, st[2], st[3]);
     const float4* a4 = nullptr;
     const float4* b4 = nullptr;
     const __half* erow = nullptr;
@@ -141,16 +143,19 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
     for (int i = 0; i < NV4; ++i) {
         const int i4 = i * kGlueThreads + tid;
         const bool ok = i4 < K4;
-        va[i] = zero4; vb[i] = zero4; vw[i] = zero4; vh[i] = zero4;
-        if (ok) {
-            if (erow) va[i] = load_param4<__half>(erow, i4);
+        va[i] = zero4; vb[i] = zero4;
+        if (ok) {  // parameter vectors stay raw until used (a conversion right here would serialise the round trips)
+            if (erow) ve[i] = fused::ldraw4<__half>(erow, i4);
             if (a4) va[i] = a4[i4];
             if (b4) vb[i] = b4[i4];
-            if (norm_mode) vw[i] = load_param4<TP>(static_cast<const TP*>(A.ln_w), i4);
-            if (need_h) vh[i] = load_param4<TP>(static_cast<const TP*>(A.h[p]), i4);
+            if (norm_mode) vw[i] = fused::ldraw4<TP>(static_cast<const TP*>(A.ln_w), i4);
+            if (need_h) vh[i] = fused::ldraw4<TP>(static_cast<const TP*>(A.h[p]), i4);
         }
     }
     // ---- LayerNorm statistics of the producer(s) (bitnet.py:118), from the GEMV's per-CTA partials
+    // (loaded after the big loads in program order: their fp64 conversion stalls the warp until they return)
+    if (A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL) load_stat_partials(A.stats_a, A.ncta_a, A.M, m, st[0], st[1]);
+    if (A.mode == GLUE_SILU_MUL) load_stat_partials(A.stats_b, A.ncta_b, A.M, m, st[2], st[3]);
     float mean_a = 0.f, rstd_a = 1.f, mean_b = 0.f, rstd_b = 1.f;
     if (A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL) {
         block_reduce_sum<4>(st, shd);
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
         for (int i = 0; i < NV4; ++i) {
             const int i4 = i * kGlueThreads + tid;
             if (i4 < K4) {
-                float4 r = va[i];
+                float4 r = A.mode == GLUE_EMBED_NORM ? fused::cvt4(ve[i]) : va[i];
                 if (A.mode == GLUE_RESID_NORM) {  // residual + LayerNorm(o / down output), :912 / :918
                     r.x = vb[i].x + (va[i].x - mean_a) * rstd_a; r.y = vb[i].y + (va[i].y - mean_a) * rstd_a;
                     r.z = vb[i].z + (va[i].z - mean_a) * rstd_a; r.w = vb[i].w + (va[i].w - mean_a) * rstd_a;
@@ -180,7 +185,10 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
         const float rr = rsqrtf((float)(ss[0] / (double)K) + A.rms_eps);  // LlamaRMSNorm :77-78
 #pragma unroll
         for (int i = 0; i < NV4; ++i) {
-            va[i].x *= rr * vw[i].x; va[i].y *= rr * vw[i].y; va[i].z *= rr * vw[i].z; va[i].w *= rr * vw[i].w;
+            if (i * kGlueThreads + tid < K4) {
+                const float4 w4 = fused::cvt4(vw[i]);
+                va[i].x *= rr * w4.x; va[i].y *= rr * w4.y; va[i].z *= rr * w4.z; va[i].w *= rr * w4.w;
+            }
         }
     } else if (A.mode == GLUE_SILU_MUL) {
 #pragma unroll
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float g = (a[e] - mean_a) * rstd_a, u = (b[e] - mean_b) * rstd_b;
-                o[e] = g / (1.f + expf(-g)) * u;  // act_fn(gate) * up, modeling_bitllama.py:257
+                o[e] = __fdividef(g, 1.f + __expf(-g)) * u;  // act_fn(gate) * up, modeling_bitllama.py:257
             }
             va[i] = make_float4(o[0], o[1], o[2], o[3]);
         }
@@ -216,7 +224,8 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
     for (int i = 0; i < NV4; ++i) {
         const int i4 = i * kGlueThreads + tid;
         if (i4 < K4) {
-            const float4 v = make_float4(va[i].x * vh[i].x, va[i].y * vh[i].y, va[i].z * vh[i].z, va[i].w * vh[i].w);
+            const float4 h4 = fused::cvt4(vh[i]);
+            const float4 v = make_float4(va[i].x * h4.x, va[i].y * h4.y, va[i].z * h4.z, va[i].w * h4.w);
             reinterpret_cast<float4*>(xs)[i4] = v;
             am = fmaxf(am, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
@@ -459,6 +468,70 @@ int glue_launch(const onebit_decoder* D, GlueArgs& g, cudaStream_t s) {
     });
 }
 
+// ---- fused glue + GEMV stage (fused_gemv.cuh) -----------------------------------------------------------
+bool fused_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ONEBIT_FUSED");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// rows per CTA so that the whole launch is about one wave of fat CTAs; returns 0 if this shape cannot use the stage
+int fused_rows_per_cta(int total_rows, int M, int K) {
+    const int sms = num_sms();
+    int rows = ((total_rows + sms - 1) / sms + 31) / 32 * 32;
+    if (rows < 32) rows = 32;
+    if (rows > 192) rows = 192;
+    if (M > 2 || fused::smem_bytes(M, K, rows) > 224 * 1024) return 0;
+    return rows;
+}
+
+template <typename TP, int TILES, int NV4>
+int fused_launch_inst2(const fused::Args& a, int ctas, cudaStream_t s) {
+    auto kern = fused::fused_gemv_kernel<TP, 1, TILES, NV4>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        configured[dev] = true;
+    }
+    return launch_pdl(kern, dim3(ctas), dim3(fused::kThreads), fused::smem_bytes(a.M, a.K, a.rows_per_cta), s, a);
+}
+
+template <typename TP, int TILES>
+int fused_launch_inst(const fused::Args& a, int ctas, cudaStream_t s) {
+    const int nv4 = (a.K / 4 + fused::kThreads - 1) / fused::kThreads;
+    if (nv4 <= 2) return fused_launch_inst2<TP, TILES, 2>(a, ctas, s);
+    if (nv4 <= 3) return fused_launch_inst2<TP, TILES, 3>(a, ctas, s);
+    if (nv4 <= 6) return fused_launch_inst2<TP, TILES, 6>(a, ctas, s);
+    return fused_launch_inst2<TP, TILES, 7>(a, ctas, s);
+}
+
+// fills cta_begin, launches; returns the number of CTAs of problem 0 through *ctas_per_problem
+int fused_launch(fused::Args a, int param_dtype, cudaStream_t s, int* ctas_per_problem) {
+    int ctas = 0;
+    for (int i = 0; i < a.nprob; ++i) {
+        a.p[i].cta_begin = ctas;
+        ctas += (a.p[i].n_rows + a.rows_per_cta - 1) / a.rows_per_cta;
+    }
+    *ctas_per_problem = (a.p[0].n_rows + a.rows_per_cta - 1) / a.rows_per_cta;
+    return dispatch_dtype(param_dtype, [&](auto pt) {
+        using TP = decltype(pt);
+        switch (a.rows_per_cta / 16) {
+            case 2: return fused_launch_inst<TP, 2>(a, ctas, s);
+            case 4: return fused_launch_inst<TP, 4>(a, ctas, s);
+            case 6: return fused_launch_inst<TP, 6>(a, ctas, s);
+            case 8: return fused_launch_inst<TP, 8>(a, ctas, s);
+            case 10: return fused_launch_inst<TP, 10>(a, ctas, s);
+            case 12: return fused_launch_inst<TP, 12>(a, ctas, s);
+            default: return fail(ONEBIT_ERR_INVALID_ARGUMENT, "fused stage: unsupported rows per CTA");
+        }
+    });
+}
+
 }  // namespace
 
 extern "C" {
@@ -564,7 +637,71 @@ int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_
         ++launches;
     }
     int cur = 0;  // residual ping-pong index holding the current stream
-    for (int l = 0; l < C.num_layers; ++l) {
+    const int rq = fused_enabled() ? fused_rows_per_cta(3 * H, M, H) : 0;
+    const int ro = fused_enabled() ? fused_rows_per_cta(H, M, H) : 0;
+    const int rg = fused_enabled() ? fused_rows_per_cta(2 * I, M, H) : 0;
+    const int rd = fused_enabled() ? fused_rows_per_cta(H, M, I) : 0;
+    const bool use_fused = rq && ro && rg && rd;
+    int nc_d = cH;  // CTAs that wrote the (sum, sumsq) partials of the last down_proj
+    for (int l = 0; use_fused && l < C.num_layers; ++l) {
+        const onebit_layer_params& P = D->layers[l];
+        int nc_q = 0, nc_o = 0, nc_g = 0;
+        // ---- stage 1: (embed | resid + LN(down)) -> RMSNorm -> q,k,v
+        fused::Args f = {};
+        f.nprob = 3; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rq;
+        f.mode = l == 0 ? fused::EMBED_NORM : fused::RESID_NORM;
+        f.t_a = D->t_d; f.stats_a = D->st_d; f.ncta_a = nc_d;
+        f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1];
+        f.embed = D->embed; f.ids = D->ids; f.ln_w = P.input_layernorm; f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
+        const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
+        for (int i = 0; i < 3; ++i) {
+            f.p[i].w = reinterpret_cast<const uint8_t*>(qkv[i]->weight); f.p[i].g = qkv[i]->weight_scale;
+            f.p[i].h = qkv[i]->input_factor; f.p[i].t = D->t_qkv + (size_t)i * C.max_batch * H;
+            f.p[i].stats = D->st_qkv + (size_t)i * cH * C.max_batch * 2; f.p[i].n_rows = H;
+        }
+        rc = fused_launch(f, pd, s, &nc_q); if (rc) return rc; ++launches;
+        cur ^= 1;
+        // ---- stage 2: attention
+        AttnArgs at = {};
+        at.t_q = f.p[0].t; at.t_k = f.p[1].t; at.t_v = f.p[2].t;
+        at.stats_q = f.p[0].stats; at.stats_k = f.p[1].stats; at.stats_v = f.p[2].stats; at.ncta = nc_q;
+        at.M = M; at.H = H; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len; at.pos = D->pos;
+        at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
+        const size_t layer_cache = (size_t)C.max_batch * C.num_heads * C.max_seq_len * kHeadDim;
+        at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
+        at.out = D->attn_out; at.ln_eps = C.ln_eps;
+        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), (size_t)C.max_seq_len * sizeof(float), s, at);
+        if (rc) return rc; ++launches;
+        // ---- stage 3: attention output -> o_proj
+        f = {};
+        f.nprob = 1; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = ro; f.mode = fused::PLAIN; f.x_plain = D->attn_out;
+        f.p[0].w = reinterpret_cast<const uint8_t*>(P.o.weight); f.p[0].g = P.o.weight_scale; f.p[0].h = P.o.input_factor;
+        f.p[0].t = D->t_o; f.p[0].stats = D->st_o; f.p[0].n_rows = H;
+        rc = fused_launch(f, pd, s, &nc_o); if (rc) return rc; ++launches;
+        // ---- stage 4: resid + LN(o) -> RMSNorm -> gate, up
+        f = {};
+        f.nprob = 2; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rg; f.mode = fused::RESID_NORM;
+        f.t_a = D->t_o; f.stats_a = D->st_o; f.ncta_a = nc_o;
+        f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1]; f.ln_w = P.post_attention_layernorm;
+        f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
+        const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
+        for (int i = 0; i < 2; ++i) {
+            f.p[i].w = reinterpret_cast<const uint8_t*>(gu[i]->weight); f.p[i].g = gu[i]->weight_scale;
+            f.p[i].h = gu[i]->input_factor; f.p[i].t = D->t_gu + (size_t)i * C.max_batch * I;
+            f.p[i].stats = D->st_gu + (size_t)i * cI * C.max_batch * 2; f.p[i].n_rows = I;
+        }
+        rc = fused_launch(f, pd, s, &nc_g); if (rc) return rc; ++launches;
+        cur ^= 1;
+        // ---- stage 5: silu(LN(gate)) * LN(up) -> down_proj
+        fused::Args f5 = {};
+        f5.nprob = 1; f5.M = M; f5.K = I; f5.units = uI; f5.rows_per_cta = rd; f5.mode = fused::SILU_MUL;
+        f5.t_a = f.p[0].t; f5.stats_a = f.p[0].stats; f5.ncta_a = nc_g;
+        f5.t_b = f.p[1].t; f5.stats_b = f.p[1].stats; f5.ncta_b = nc_g; f5.ln_eps = C.ln_eps;
+        f5.p[0].w = reinterpret_cast<const uint8_t*>(P.down.weight); f5.p[0].g = P.down.weight_scale;
+        f5.p[0].h = P.down.input_factor; f5.p[0].t = D->t_d; f5.p[0].stats = D->st_d; f5.p[0].n_rows = H;
+        rc = fused_launch(f5, pd, s, &nc_d); if (rc) return rc; ++launches;
+    }
+    for (int l = 0; !use_fused && l < C.num_layers; ++l) {
         const onebit_layer_params& P = D->layers[l];
         // ---- glue 1: (embed | resid + LN(down of previous layer)) -> RMSNorm -> q/k/v digits
         GlueArgs g = {};
@@ -652,7 +789,7 @@ int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_
     // ---- final: resid + LN(down) -> RMSNorm(final) -> fp16 x -> lm_head -> argmax
     GlueArgs g = {};
     g.mode = GLUE_RESID_NORM; g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1;
-    g.t_a = D->t_d; g.stats_a = D->st_d; g.ncta_a = cH;
+    g.t_a = D->t_d; g.stats_a = D->st_d; g.ncta_a = use_fused ? nc_d : cH;
     g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = D->final_norm;
     g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps; g.x_f16 = D->x_f16;
     rc = glue_launch(D, g, s); if (rc) return rc; ++launches;
@@ -688,6 +825,52 @@ int onebit_decoder_gemv_only(onebit_decoder* D, int batch, void* stream) {
     const int uH = H / imma::kUnitCols, uI = I / imma::kUnitCols;
     const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
     const size_t dgH = (size_t)C.max_batch * uH * imma::kUnitBytes;
+    const int rq = fused_enabled() ? fused_rows_per_cta(3 * H, M, H) : 0, ro = fused_enabled() ? fused_rows_per_cta(H, M, H) : 0;
+    const int rg = fused_enabled() ? fused_rows_per_cta(2 * I, M, H) : 0, rd = fused_enabled() ? fused_rows_per_cta(H, M, I) : 0;
+    if (rq && ro && rg && rd) {  // the fused glue+GEMV stages (what the step really runs), attention skipped
+        int nc_d = cH, cur = 0;
+        for (int l = 0; l < C.num_layers; ++l) {
+            const onebit_layer_params& P = D->layers[l];
+            int nc_q = 0, nc_o = 0, nc_g = 0, rc;
+            fused::Args f = {};
+            f.nprob = 3; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rq; f.mode = fused::RESID_NORM;
+            f.t_a = D->t_d; f.stats_a = D->st_d; f.ncta_a = nc_d; f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1];
+            f.ln_w = P.input_layernorm; f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
+            const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
+            for (int i = 0; i < 3; ++i) {
+                f.p[i].w = reinterpret_cast<const uint8_t*>(qkv[i]->weight); f.p[i].g = qkv[i]->weight_scale;
+                f.p[i].h = qkv[i]->input_factor; f.p[i].t = D->t_qkv + (size_t)i * C.max_batch * H;
+                f.p[i].stats = D->st_qkv + (size_t)i * cH * C.max_batch * 2; f.p[i].n_rows = H;
+            }
+            rc = fused_launch(f, pd, s, &nc_q); if (rc) return rc;
+            cur ^= 1;
+            f = {};
+            f.nprob = 1; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = ro; f.mode = fused::PLAIN; f.x_plain = D->attn_out;
+            f.p[0].w = reinterpret_cast<const uint8_t*>(P.o.weight); f.p[0].g = P.o.weight_scale; f.p[0].h = P.o.input_factor;
+            f.p[0].t = D->t_o; f.p[0].stats = D->st_o; f.p[0].n_rows = H;
+            rc = fused_launch(f, pd, s, &nc_o); if (rc) return rc;
+            f = {};
+            f.nprob = 2; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rg; f.mode = fused::RESID_NORM;
+            f.t_a = D->t_o; f.stats_a = D->st_o; f.ncta_a = nc_o; f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1];
+            f.ln_w = P.post_attention_layernorm; f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
+            const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
+            for (int i = 0; i < 2; ++i) {
+                f.p[i].w = reinterpret_cast<const uint8_t*>(gu[i]->weight); f.p[i].g = gu[i]->weight_scale;
+                f.p[i].h = gu[i]->input_factor; f.p[i].t = D->t_gu + (size_t)i * C.max_batch * I;
+                f.p[i].stats = D->st_gu + (size_t)i * cI * C.max_batch * 2; f.p[i].n_rows = I;
+            }
+            rc = fused_launch(f, pd, s, &nc_g); if (rc) return rc;
+            cur ^= 1;
+            fused::Args f5 = {};
+            f5.nprob = 1; f5.M = M; f5.K = I; f5.units = uI; f5.rows_per_cta = rd; f5.mode = fused::SILU_MUL;
+            f5.t_a = f.p[0].t; f5.stats_a = f.p[0].stats; f5.ncta_a = nc_g; f5.t_b = f.p[1].t; f5.stats_b = f.p[1].stats;
+            f5.ncta_b = nc_g; f5.ln_eps = C.ln_eps;
+            f5.p[0].w = reinterpret_cast<const uint8_t*>(P.down.weight); f5.p[0].g = P.down.weight_scale;
+            f5.p[0].h = P.down.input_factor; f5.p[0].t = D->t_d; f5.p[0].stats = D->st_d; f5.p[0].n_rows = H;
+            rc = fused_launch(f5, pd, s, &nc_d); if (rc) return rc;
+        }
+        return ONEBIT_OK;
+    }
     for (int l = 0; l < C.num_layers; ++l) {
         const onebit_layer_params& P = D->layers[l];
         imma::Args a = {};
@@ -738,3 +921,14 @@ int onebit_decoder_step_host(onebit_decoder* D, int batch, const int64_t* ids_ho
 }
 
 }  // extern "C"
+
+// Debug only (side builds with -DONEBIT_TRACE): stamps written by the kernels instantiated in THIS translation unit
+// (fused stages); matvec_mma.cu has its own copy for the stand-alone GEMV.
+extern "C" __attribute__((visibility("default"))) int onebit_debug_read_trace_decoder(long long* out8) {
+#ifdef ONEBIT_TRACE
+    return cudaMemcpyFromSymbol(out8, onebit::imma::g_trace, sizeof(long long) * 8) == cudaSuccess ? 0 : -2;
+#else
+    (void)out8;
+    return -1;
+#endif
+}

@@ -37,7 +37,7 @@ namespace imma {
 
 #ifdef ONEBIT_TRACE
 __device__ long long g_trace[8];
-#define TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_trace[i] = clock64(); } while (0)
+#define TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) ::onebit::imma::g_trace[i] = clock64(); } while (0)
 #else
 #define TR(i)
 #endif
@@ -130,7 +130,7 @@ inline size_t gemv_smem_bytes(int M, int units, int NT) {
 template <typename TP, int NT, int UPW>
 __global__ void __launch_bounds__(kThreads, (NT == 1 && UPW <= 3) ? 5 : 2) gemv_kernel(const __grid_constant__ Args A) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[UPW];  // one per round of 8 units: the IMMA loop starts on the first 8 KB
     const int M = A.M;
     unsigned char* Bs = smem;                                                          // [M][units][1024]
     int* red = reinterpret_cast<int*>(smem + (size_t)M * A.units * kUnitBytes);       // [kWarps][32][8*NT]
@@ -163,13 +163,14 @@ __global__ void __launch_bounds__(kThreads, (NT == 1 && UPW <= 3) ? 5 : 2) gemv_
         }
     }
     if (tid == 0) {
-        mbar_init(&s_bar, 1);
+#pragma unroll
+        for (int r8 = 0; r8 < UPW; ++r8) mbar_init(&s_bar[r8], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // epilogue operands: this thread finalises (row = tid & 31, token = tid >> 5); g is static -> load it now
     const int er = tid & 31, em = tid >> 5;
-    float gval = 1.f;
-    if (P.g != nullptr && row0 + er < P.n_rows) gval = to_f32(static_cast<const TP*>(P.g)[row0 + er]);
+    TP graw = from_f32<TP>(1.f);  // converted at use: a conversion here would wait for the load
+    if (P.g != nullptr && row0 + er < P.n_rows) graw = static_cast<const TP*>(P.g)[row0 + er];
     TR(1);
     pdl_launch_dependents();
     pdl_wait();  // producer's digits / qmeta are now visible
@@ -179,17 +180,23 @@ __global__ void __launch_bounds__(kThreads, (NT == 1 && UPW <= 3) ? 5 : 2) gemv_
     qm.qtot = 0;
     if (em < M) qm = P.qmeta[em];
 
-    // ---- 2. activation digits: one bulk copy into shared memory ----
-    const uint32_t dbytes = (uint32_t)M * A.units * kUnitBytes;
+    // ---- 2. activation digits: bulk (TMA) copies into shared memory, one mbarrier per round of 8 units ----
     if (tid == 0) {
-        mbar_expect_tx(&s_bar, dbytes);
-        bulk_g2s(Bs, P.digits, dbytes, &s_bar);
+#pragma unroll
+        for (int r8 = 0; r8 < UPW; ++r8) {
+            const int u0 = r8 * kWarps, nu = min(kWarps, A.units - u0);
+            if (nu > 0) {
+                mbar_expect_tx(&s_bar[r8], (uint32_t)(M * nu * kUnitBytes));
+                for (int m = 0; m < M; ++m)
+                    bulk_g2s(Bs + (size_t)(m * A.units + u0) * kUnitBytes, P.digits + (size_t)(m * A.units + u0) * kUnitBytes,
+                             (uint32_t)(nu * kUnitBytes), &s_bar[r8]);
+            }
+        }
     }
-    __syncthreads();  // barrier init visible to all waiters
-    mbar_wait(&s_bar, 0);
+    __syncthreads();  // barrier inits visible to all waiters
     TR(3);
 
-    // two independent accumulator sets per row tile (even / odd plane pairs) halve the IMMA dependency chains
+    // two independent accumulator sets per row tile (even / odd planes): 4 interleaved IMMA dependency chains
     int acc2[2][2][NT][4];
 #pragma unroll
     for (int z = 0; z < 2; ++z)
@@ -205,6 +212,7 @@ __global__ void __launch_bounds__(kThreads, (NT == 1 && UPW <= 3) ? 5 : 2) gemv_
     for (int s = 0; s < UPW; ++s) {
         const int u = warp + s * kWarps;
         if (u < A.units) {
+            mbar_wait(&s_bar[s], 0);
 #pragma unroll
             for (int jp = 0; jp < 4; ++jp) {
                 uint4 bv[NT];
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, (NT == 1 && UPW <= 3) ? 5 : 2) gemv_
                         const uint32_t a2 = plane(wreg[s][2 * r].y, mask), a3 = plane(wreg[s][2 * r + 1].y, mask);
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt)
-                            imma16832(acc2[jp & 1][r][nt], a0, a1, a2, a3, jj ? bv[nt].z : bv[nt].x,
+                            imma16832(acc2[jj][r][nt], a0, a1, a2, a3, jj ? bv[nt].z : bv[nt].x,
                                       jj ? bv[nt].w : bv[nt].y);
                     }
                 }
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, (NT == 1 && UPW <= 3) ? 5 : 2) gemv_
         const long long V = (((long long)a.w * 256 + a.z) * 256 + a.y) * 256 + a.x;  // = 128 * sum_{bit=1} q
         float val = (float)((double)(qm.qtot - 2 * (V >> 7)) * qm.inv_scale);
         if (n < P.n_rows) {
-            val *= gval;
+            val *= to_f32(graw);
             P.t[(size_t)m * P.ld_t + n] = val;
             su = val;
             sq = val * val;

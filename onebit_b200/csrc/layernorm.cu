@@ -25,6 +25,101 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
     return r;
 }
 
+template <typename T>
+__device__ __forceinline__ float4 load4_as_f32(const T* p, int64_t i4);
+template <>
+__device__ __forceinline__ float4 load4_as_f32<float>(const float* p, int64_t i4) {
+    return reinterpret_cast<const float4*>(p)[i4];
+}
+template <>
+__device__ __forceinline__ float4 load4_as_f32<__half>(const __half* p, int64_t i4) {
+    const uint2 r = reinterpret_cast<const uint2*>(p)[i4];
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <>
+__device__ __forceinline__ float4 load4_as_f32<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i4) {
+    const uint2 r = reinterpret_cast<const uint2*>(p)[i4];
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T>
+__device__ __forceinline__ void store4_from_f32(T* p, int64_t i4, float4 v);
+template <>
+__device__ __forceinline__ void store4_from_f32<float>(float* p, int64_t i4, float4 v) {
+    reinterpret_cast<float4*>(p)[i4] = v;
+}
+template <>
+__device__ __forceinline__ void store4_from_f32<__half>(__half* p, int64_t i4, float4 v) {
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(p)[i4] = pk;
+}
+template <>
+__device__ __forceinline__ void store4_from_f32<__nv_bfloat16>(__nv_bfloat16* p, int64_t i4, float4 v) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(p)[i4] = pk;
+}
+
+// Vectorised variant for N % 4 == 0 and N <= 4 * NV4 * blockDim: the row lives in NV4 float4 registers per
+// thread, all loads are issued before the first reduction (this is the variant every LLaMA shape takes).
+template <typename TY, typename TP, int NV4, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+scale_layernorm_vec_kernel(const float* __restrict__ t, const TP* __restrict__ g, const TP* __restrict__ bias,
+                           TY* __restrict__ y, int64_t N, float eps) {
+    __shared__ float sh[THREADS / 32];
+    const int64_t m = blockIdx.x, N4 = N >> 2;
+    const float* row = t + m * N;
+    float4 u[NV4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int64_t i4 = (int64_t)i * THREADS + threadIdx.x;
+        u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < N4) {
+            float4 v = reinterpret_cast<const float4*>(row)[i4];
+            if (g) {
+                const float4 gv = load4_as_f32<TP>(g, i4);
+                v.x *= gv.x; v.y *= gv.y; v.z *= gv.z; v.w *= gv.w;
+            }
+            u[i] = v;
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    }
+    const float mean = block_sum(s, sh) / (float)N;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int64_t i4 = (int64_t)i * THREADS + threadIdx.x;
+        if (i4 < N4) {
+            const float a = u[i].x - mean, b = u[i].y - mean, c = u[i].z - mean, d = u[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float var = block_sum(q, sh) / (float)N;
+    const float rstd = rsqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int64_t i4 = (int64_t)i * THREADS + threadIdx.x;
+        if (i4 < N4) {
+            float4 v = make_float4((u[i].x - mean) * rstd, (u[i].y - mean) * rstd, (u[i].z - mean) * rstd,
+                                   (u[i].w - mean) * rstd);
+            if (bias) {
+                const float4 bv = load4_as_f32<TP>(bias, i4);
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            }
+            store4_from_f32<TY>(y + m * N, i4, v);
+        }
+    }
+}
+
 template <typename TY, typename TP>
 __global__ void __launch_bounds__(kLnThreads)
 scale_layernorm_kernel(const float* __restrict__ t, const TP* __restrict__ g, const TP* __restrict__ bias,
@@ -144,8 +239,18 @@ int launch_scale_layernorm(const float* t, const void* g, const void* bias, void
         using TY = decltype(yt);
         return dispatch_dtype(param_dtype, [&](auto pt) {
             using TP = decltype(pt);
-            scale_layernorm_kernel<TY, TP><<<(unsigned)m, kLnThreads, 0, s>>>(
-                t, static_cast<const TP*>(g), static_cast<const TP*>(bias), static_cast<TY*>(y), n, eps);
+            const TP* gp = static_cast<const TP*>(g);
+            const TP* bp = static_cast<const TP*>(bias);
+            TY* yp = static_cast<TY*>(y);
+            const int64_t n4 = n / 4;
+            if (n % 4 == 0 && n4 <= 2 * 256)
+                scale_layernorm_vec_kernel<TY, TP, 2, 256><<<(unsigned)m, 256, 0, s>>>(t, gp, bp, yp, n, eps);
+            else if (n % 4 == 0 && n4 <= 4 * 256)
+                scale_layernorm_vec_kernel<TY, TP, 4, 256><<<(unsigned)m, 256, 0, s>>>(t, gp, bp, yp, n, eps);
+            else if (n % 4 == 0 && n4 <= 8 * 512)
+                scale_layernorm_vec_kernel<TY, TP, 8, 512><<<(unsigned)m, 512, 0, s>>>(t, gp, bp, yp, n, eps);
+            else
+                scale_layernorm_kernel<TY, TP><<<(unsigned)m, kLnThreads, 0, s>>>(t, gp, bp, yp, n, eps);
             ONEBIT_CUDA_TRY(cudaGetLastError());
             return ONEBIT_OK;
         });

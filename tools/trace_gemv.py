@@ -18,7 +18,9 @@ names = ["start->weights issued", "->pdl wait entered", "->wait done", "->digits
 for rep in range(5):
     dec.step()
     torch.cuda.synchronize()
-    assert lib.onebit_debug_read_trace(out) == 0
-    t = list(out)[:6]
-    print("last GEMV of the step (down_proj, K=11008, 128 CTAs), cycles:", [t[i + 1] - t[i] for i in range(5)], "total", t[5] - t[0])
+    import os
+    fn = lib.onebit_debug_read_trace_decoder if os.environ.get('ONEBIT_FUSED', '1') != '0' else lib.onebit_debug_read_trace
+    assert fn(out) == 0
+    t = list(out)[:8]
+    print("last GEMV-stage of the step (down_proj), stage cycles:", [t[i + 1] - t[i] for i in range(7)], "total", t[7] - t[0])
 g = torch.cuda.CUDAGraph()
