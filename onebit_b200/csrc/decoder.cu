@@ -11,6 +11,7 @@
 // glue(resid+norm -> gate/up digits) | GEMV gate,up | glue(silu*up -> down digits) | GEMV down.
 // All state that changes between steps (token ids, positions) lives in device memory, so a step is one
 // CUDA graph replay. The residual stream is kept in fp32.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <new>
@@ -245,17 +246,35 @@ struct AttnArgs {
     __half* kcache; __half* vcache; // [M_max][n_heads][max_seq][kHeadDim] for this layer
     float* out;                     // [M][H] fp32
     float ln_eps;
+    int t_cap;                      // cache rows that fit in shared memory (bulk-copied up front); longer contexts stream
 };
 
 __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ AttnArgs A) {
-    extern __shared__ __align__(16) float sc[];  // [T] scores
-    __shared__ float qs[kHeadDim];
+    extern __shared__ __align__(16) float sc[];  // [max(max_seq, 512)] scores, then K rows, then V rows (fp16)
+    __shared__ __align__(8) uint64_t kv_bar;
+    __shared__ __align__(16) float qs[kHeadDim];
     __shared__ double shd[33 * 6];
     __shared__ float red[kHeadDim / 32];
     imma::pdl_launch_dependents();
     imma::pdl_wait();
     const int m = blockIdx.x, hd = blockIdx.y, d = threadIdx.x, lane = d & 31, warp = d >> 5;
     const int pos = A.pos[m], T = pos + 1;
+    __half* kc = A.kcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
+    __half* vc = A.vcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
+    // The cached rows 0..pos-1 of this (sequence, head) are contiguous: pull them into shared memory with two bulk
+    // (TMA) copies issued before anything else, so the score and P.V loops never wait on a global load.
+    const bool in_smem = T <= A.t_cap;
+    __half* Ks = reinterpret_cast<__half*>(sc + max(A.max_seq, 4 * kHeadDim));
+    __half* Vs = Ks + (size_t)A.t_cap * kHeadDim;
+    if (d == 0) {
+        imma::mbar_init(&kv_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (in_smem && pos > 0) {
+            imma::mbar_expect_tx(&kv_bar, (uint32_t)(2 * pos * kHeadDim * 2));
+            imma::bulk_g2s(Ks, kc, (uint32_t)(pos * kHeadDim * 2), &kv_bar);
+            imma::bulk_g2s(Vs, vc, (uint32_t)(pos * kHeadDim * 2), &kv_bar);
+        }
+    }
     float mq, rq, mk, rk, mv, rv;
     {
         double st[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -276,21 +295,37 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     const float qr = d < half ? q0 * c - q1 * s : q0 * c + q1 * s;
     const float kr = d < half ? k0 * c - k1 * s : k0 * c + k1 * s;
     const float vv = (A.t_v[col + d] - mv) * rv;
-    __half* kc = A.kcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
-    __half* vc = A.vcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
     kc[(size_t)pos * kHeadDim + d] = __float2half_rn(kr);
     vc[(size_t)pos * kHeadDim + d] = __float2half_rn(vv);
+    if (in_smem) {
+        Ks[(size_t)pos * kHeadDim + d] = __float2half_rn(kr);
+        Vs[(size_t)pos * kHeadDim + d] = __float2half_rn(vv);
+    }
     qs[d] = qr * 0.08838834764831845f;  // 1/sqrt(128), :546
     __syncthreads();
-    // scores: one warp per cached position, lanes over d (4 each)
+    if (in_smem && pos > 0) imma::mbar_wait(&kv_bar, 0);
+    const __half* kr_base = in_smem ? Ks : kc;
+    const __half* vr_base = in_smem ? Vs : vc;
+    // scores: one warp per cached position, lanes over d (4 each); 4 positions in flight per warp
     const float4 qv = *reinterpret_cast<const float4*>(&qs[4 * lane]);
-    for (int j = warp; j < T; j += kHeadDim / 32) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(kc + (size_t)j * kHeadDim + 4 * lane);
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-        float dot = qv.x * a.x + qv.y * a.y + qv.z * b.x + qv.w * b.y;
-        dot = warp_sum(dot);
-        if (lane == 0) sc[j] = dot;
+    constexpr int NW = kHeadDim / 32;
+    for (int j0 = warp; j0 < T; j0 += 4 * NW) {
+        uint2 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * NW;
+            raw[u] = make_uint2(0u, 0u);
+            if (j < T) raw[u] = *reinterpret_cast<const uint2*>(kr_base + (size_t)j * kHeadDim + 4 * lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * NW;
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].y));
+            float dot = qv.x * a.x + qv.y * a.y + qv.z * b.x + qv.w * b.y;
+            dot = warp_sum(dot);
+            if (lane == 0 && j < T) sc[j] = dot;
+        }
     }
     __syncthreads();
     float mx = -INFINITY;
@@ -311,8 +346,34 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     if (lane == 0) red[warp] = sum;
     __syncthreads();
     const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+    // P.V: warp w takes positions w, w+4, ...; lane holds dims 4*lane .. 4*lane+3; partials combined through smem
+    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = warp; j0 < T; j0 += 4 * NW) {
+        uint2 raw[4];
+        float pj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * NW;
+            raw[u] = make_uint2(0u, 0u);
+            pj[u] = 0.f;
+            if (j < T) {
+                raw[u] = *reinterpret_cast<const uint2*>(vr_base + (size_t)j * kHeadDim + 4 * lane);
+                pj[u] = sc[j];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].y));
+            pv.x += pj[u] * a.x; pv.y += pj[u] * a.y; pv.z += pj[u] * b.x; pv.w += pj[u] * b.y;
+        }
+    }
+    __syncthreads();  // sc is dead from here on: reuse it for the cross-warp partials [NW][kHeadDim]
+    *reinterpret_cast<float4*>(&sc[warp * kHeadDim + 4 * lane]) = pv;
+    __syncthreads();
     float acc = 0.f;
-    for (int j = 0; j < T; ++j) acc += sc[j] * __half2float(vc[(size_t)j * kHeadDim + d]);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) acc += sc[w * kHeadDim + d];
     A.out[col + d] = acc * inv;
 }
 
@@ -466,6 +527,16 @@ int glue_launch(const onebit_decoder* D, GlueArgs& g, cudaStream_t s) {
         if (nv4 <= 6) return glue_launch_inst<TP, 6>(g, s);
         return glue_launch_inst<TP, 7>(g, s);
     });
+}
+
+size_t attn_smem_bytes(int max_seq) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        configured[dev] = true;
+    }
+    return (size_t)std::max(max_seq, 4 * kHeadDim) * sizeof(float) + (size_t)2 * std::min(max_seq, 384) * kHeadDim * 2;
 }
 
 // ---- fused glue + GEMV stage (fused_gemv.cuh) -----------------------------------------------------------
@@ -669,8 +740,8 @@ int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_
         at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
         const size_t layer_cache = (size_t)C.max_batch * C.num_heads * C.max_seq_len * kHeadDim;
         at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
-        at.out = D->attn_out; at.ln_eps = C.ln_eps;
-        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), (size_t)C.max_seq_len * sizeof(float), s, at);
+        at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = std::min(C.max_seq_len, 384);
+        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), attn_smem_bytes(C.max_seq_len), s, at);
         if (rc) return rc; ++launches;
         // ---- stage 3: attention output -> o_proj
         f = {};
@@ -734,8 +805,8 @@ int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_
         at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
         const size_t layer_cache = (size_t)C.max_batch * C.num_heads * C.max_seq_len * kHeadDim;
         at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
-        at.out = D->attn_out; at.ln_eps = C.ln_eps;
-        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), (size_t)C.max_seq_len * sizeof(float), s, at);
+        at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = std::min(C.max_seq_len, 384);
+        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), attn_smem_bytes(C.max_seq_len), s, at);
         if (rc) return rc; ++launches;
         // ---- glue 2: attention output -> o digits
         g = {};

@@ -197,23 +197,32 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemv_kernel(const __grid_co
         for (int r = lane; r < rows_here; r += 32)
             imma::bulk_g2s(Ws + (size_t)r * pitch, P.w + (size_t)(row0 + r) * Kb, (uint32_t)Kb, &s_bar);
     }
+    // static parameter vectors (input_factor, RMSNorm weight) are loaded raw BEFORE the dependency wait as well
+    const TP* hptr = static_cast<const TP*>(P.h);
+    const TP* lnw = static_cast<const TP*>(A.ln_w);
+    const bool norm_mode = A.mode == EMBED_NORM || A.mode == RESID_NORM;
+    Raw4<TP> vh[NV4], vw[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+        const int i4 = i * kThreads + tid;
+        if (i4 < K4) {
+            vh[i] = ldraw4<TP>(hptr, i4);
+            if (norm_mode) vw[i] = ldraw4<TP>(lnw, i4);
+        }
+    }
+    TP graw = from_f32<TP>(1.f);  // weight_scale of the row this thread finalises (static: load now, convert at use)
+    if (tid < rows_here) graw = static_cast<const TP*>(P.g)[row0 + tid];
     imma::pdl_launch_dependents();
     imma::pdl_wait();
     TR(1);
 
     // ---- 2. rebuild the BitLinear input (glue), per token: x' -> digits in shared memory ----
     // Every global load of a token is issued before the first use (one exposed L2 round trip), NV4 float4 per array.
-    const TP* hptr = static_cast<const TP*>(P.h);
-    const TP* lnw = static_cast<const TP*>(A.ln_w);
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    TP graw = from_f32<TP>(1.f);  // weight_scale of the row this thread finalises (static: load now, convert at use)
-    if (tid < rows_here) graw = static_cast<const TP*>(P.g)[row0 + tid];
     for (int m = 0; m < M; ++m) {
         float4 va[NV4], vb[NV4];
-        Raw4<TP> vh[NV4], vw[NV4];
         Raw4<__half> ve[NV4];
         double st[4] = {0.0, 0.0, 0.0, 0.0};
-        const bool norm_mode = A.mode == EMBED_NORM || A.mode == RESID_NORM;
         {
             const __half* erow = A.mode == EMBED_NORM ? A.embed + (size_t)A.ids[m] * K : nullptr;
             const float4* a4 = reinterpret_cast<const float4*>(
@@ -228,8 +237,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemv_kernel(const __grid_co
                     if (erow) ve[i] = ldraw4<__half>(erow, i4);
                     else va[i] = a4[i4];
                     if (b4) vb[i] = b4[i4];
-                    vh[i] = ldraw4<TP>(hptr, i4);
-                    if (norm_mode) vw[i] = ldraw4<TP>(lnw, i4);
                 }
             }
         }
