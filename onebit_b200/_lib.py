@@ -20,6 +20,8 @@ VARIANTS = {"auto": VARIANT_AUTO, "simt": VARIANT_SIMT, "mma": VARIANT_MMA, "tc5
 _c = ctypes
 _vp, _i64, _int, _f32, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_size_t
 
+ALLREDUCE_FN = _c.CFUNCTYPE(_int, _vp, _vp, _i64, _vp)  # int (*)(void* user, float* data, int64 count, void* stream)
+
 # name -> (restype, argtypes); must list every symbol include/onebit_b200.h declares (checked by tests)
 SIGNATURES = {
     "onebit_version": (_c.c_char_p, []),
@@ -40,7 +42,7 @@ SIGNATURES = {
     "onebit_layer_forward_host": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "onebit_layer_forward_device": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "onebit_layer_destroy": (None, [_vp]),
-    "onebit_decoder_create": (_int, [_c.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "onebit_decoder_create": (_int, [_c.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp, ALLREDUCE_FN, _vp]),
     "onebit_decoder_reset": (_int, [_vp, _vp, _vp, _int, _vp]),
     "onebit_decoder_step": (_int, [_vp, _int, _vp, _vp, _vp]),
     "onebit_decoder_step_host": (_int, [_vp, _int, _vp, _vp, _vp]),

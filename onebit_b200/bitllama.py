@@ -40,7 +40,8 @@ class BitLlamaDecoderB200:
     """
 
     def __init__(self, config: Dict, state_dict: Dict[str, torch.Tensor], device="cuda:0", max_seq_len: int = 2048,
-                 max_batch: int = 1, param_dtype: torch.dtype = torch.float16, use_graph: bool = True):
+                 max_batch: int = 1, param_dtype: torch.dtype = torch.float16, use_graph: bool = True,
+                 tp_group=None):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -67,6 +68,26 @@ class BitLlamaDecoderB200:
             self._keep.append(t)
             return t
 
+        # tensor parallelism: shard the state dict for this rank (o/down K shards zero-padded), all-reduce through
+        # torch.distributed on the current stream (NCCL; capturable in the step's CUDA graph)
+        self.tp_size, self.tp_rank, self._ar_cb = 1, 0, None
+        if tp_group is not None:
+            import torch.distributed as dist
+            from .tp import shard_state_dict
+            self.tp_size, self.tp_rank = dist.get_world_size(tp_group), dist.get_rank(tp_group)
+            if self.tp_size > 1:
+                state_dict = shard_state_dict(config, state_dict, self.tp_size, self.tp_rank)
+
+                def _allreduce(user, ptr, count, stream):
+                    try:
+                        t = _tensor_from_ptr(ptr, (int(count),), torch.float32, dev)
+                        dist.all_reduce(t, group=tp_group)
+                        return 0
+                    except Exception as exc:  # surfaced as an error code by the C side
+                        print(f"onebit_b200: all-reduce failed: {exc}", flush=True)
+                        return 1
+
+                self._ar_cb = _lib.ALLREDUCE_FN(_allreduce)
         sd = state_dict
         layers = (_lib.LayerParams * self.L)()
         self.weight_bytes = 0
@@ -90,13 +111,13 @@ class BitLlamaDecoderB200:
         cos, sin = rope_tables(self.H // self.n_heads, self.max_seq_len, float(config.get("rope_theta", 10000.0)))
         cos, sin = put(cos), put(sin)
         cfg = _lib.DecoderConfig(self.H, self.I, self.L, self.n_heads, self.V, self.max_seq_len, self.max_batch, pcode,
-                                 float(config.get("rms_norm_eps", 1e-6)), 1e-5, 1, 0)
+                                 float(config.get("rms_norm_eps", 1e-6)), 1e-5, self.tp_size, self.tp_rank)
         self._layers = layers
         self._handle = ctypes.c_void_p()
         with torch.cuda.device(dev):
             rc = self.lib.onebit_decoder_create(ctypes.byref(self._handle), ctypes.byref(cfg), layers, embed.data_ptr(),
                                                 final_norm.data_ptr(), lm_head.data_ptr(), cos.data_ptr(), sin.data_ptr(),
-                                                None, None)
+                                                self._ar_cb if self._ar_cb is not None else _lib.ALLREDUCE_FN(0), None)
         _lib.check(rc, "onebit_decoder_create")
         self.logits = torch.zeros((self.max_batch, self.V), dtype=torch.float32, device=dev)
         self.forced = torch.zeros((self.max_batch,), dtype=torch.int64, device=dev)

@@ -39,6 +39,7 @@ enum GlueMode {
 
 struct GlueArgs {
     int mode, M, K, nprob, write_x_f16;
+    int stats_from_data;  // RESID_NORM: t_a was all-reduced across ranks -> (sum, sumsq) from the data itself
     const float* t_a; const float* stats_a; int ncta_a;   // previous GEMV output (already * g), [ncta][M][2] partials
     const float* t_b; const float* stats_b; int ncta_b;
     const float* resid_in; float* resid_out;              // [M][K] fp32
@@ -155,8 +156,17 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
     }
     // ---- LayerNorm statistics of the producer(s) (bitnet.py:118), from the GEMV's per-CTA partials
     // (loaded after the big loads in program order: their fp64 conversion stalls the warp until they return)
-    if (A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL) load_stat_partials(A.stats_a, A.ncta_a, A.M, m, st[0], st[1]);
+    if ((A.mode == GLUE_RESID_NORM && !A.stats_from_data) || A.mode == GLUE_SILU_MUL)
+        load_stat_partials(A.stats_a, A.ncta_a, A.M, m, st[0], st[1]);
     if (A.mode == GLUE_SILU_MUL) load_stat_partials(A.stats_b, A.ncta_b, A.M, m, st[2], st[3]);
+    if (A.mode == GLUE_RESID_NORM && A.stats_from_data) {
+#pragma unroll
+        for (int i = 0; i < NV4; ++i)
+            if (i * kGlueThreads + tid < K4) {
+                st[0] += (double)((va[i].x + va[i].y) + (va[i].z + va[i].w));
+                st[1] += (double)((va[i].x * va[i].x + va[i].y * va[i].y) + (va[i].z * va[i].z + va[i].w * va[i].w));
+            }
+    }
     float mean_a = 0.f, rstd_a = 1.f, mean_b = 0.f, rstd_b = 1.f;
     if (A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL) {
         block_reduce_sum<4>(st, shd);
@@ -240,7 +250,8 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
 struct AttnArgs {
     const float* t_q; const float* t_k; const float* t_v;  // [M][H] fp32 (already * g)
     const float* stats_q; const float* stats_k; const float* stats_v; int ncta;  // per-CTA partials of each projection
-    int M, H, n_heads, max_seq;
+    int M, H, n_heads, max_seq;   // H = row stride of t_q/t_k/t_v (local width under tensor parallelism)
+    int n_ln, out_ld;            // rows of the FULL q/k/v layers (LayerNorm denominator); row stride of `out`
     const int* pos;                 // [M] device
     const float* rope_cos; const float* rope_sin;  // [max_seq][kHeadDim/2]
     __half* kcache; __half* vcache; // [M_max][n_heads][max_seq][kHeadDim] for this layer
@@ -282,9 +293,9 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
         load_stat_partials(A.stats_k, A.ncta, A.M, m, st[2], st[3]);
         load_stat_partials(A.stats_v, A.ncta, A.M, m, st[4], st[5]);
         block_reduce_sum<6>(st, shd);
-        finish_ln(st[0], st[1], A.H, A.ln_eps, mq, rq);
-        finish_ln(st[2], st[3], A.H, A.ln_eps, mk, rk);
-        finish_ln(st[4], st[5], A.H, A.ln_eps, mv, rv);
+        finish_ln(st[0], st[1], A.n_ln, A.ln_eps, mq, rq);
+        finish_ln(st[2], st[3], A.n_ln, A.ln_eps, mk, rk);
+        finish_ln(st[4], st[5], A.n_ln, A.ln_eps, mv, rv);
     }
     const size_t col = (size_t)m * A.H + hd * kHeadDim;
     const int half = kHeadDim / 2, dp = d < half ? d + half : d - half, fi = d < half ? d : d - half;
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < NW; ++w) acc += sc[w * kHeadDim + d];
-    A.out[col + d] = acc * inv;
+    A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = acc * inv;
 }
 
 // ---- lm_head: logits[m][v] = sum_k W[v][k] * x[m][k], fp16 weights, fp32 accumulate (:1610-1611) ----
@@ -456,6 +467,24 @@ __global__ void copy_ids_kernel(const long long* src, long long* dst, int n) {
     if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
 }
 
+// Sum the per-CTA (sum, sumsq) partials of `nproj` projections into [nproj][M][2] floats (fixed order) so that a
+// tensor-parallel run can all-reduce a handful of floats; consumers then read them as a single "CTA".
+__global__ void __launch_bounds__(256) reduce_stats_kernel(const float* __restrict__ stats, int proj_stride, int ncta,
+                                                          int M, float* __restrict__ out) {
+    __shared__ double shd[33 * 2];
+    imma::pdl_launch_dependents();
+    imma::pdl_wait();
+    const int p = blockIdx.x / M, m = blockIdx.x % M;
+    double st[2] = {0.0, 0.0};
+    for (int c = threadIdx.x; c < ncta; c += blockDim.x) {
+        const float2 v = *reinterpret_cast<const float2*>(stats + (size_t)p * proj_stride + ((size_t)c * M + m) * 2);
+        st[0] += (double)v.x;
+        st[1] += (double)v.y;
+    }
+    block_reduce_sum<2>(st, shd);
+    if (threadIdx.x == 0) *reinterpret_cast<float2*>(out + ((size_t)p * M + m) * 2) = make_float2((float)st[0], (float)st[1]);
+}
+
 template <typename... KArgs, typename... Args>
 int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -499,6 +528,9 @@ struct onebit_decoder {
     long long* ids_stage = nullptr;
     int* pos = nullptr;
     int launches = 0;
+    // tensor-parallel geometry (tp = 1: Hl = Hk = H, Il = Ik = I)
+    int tp = 1, Hl = 0, Hk = 0, Il = 0, Ik = 0, heads_l = 0;
+    float *red_qkv = nullptr, *red_gu = nullptr;  // [nproj][max_batch][2] all-reduced (sum, sumsq)
 };
 
 namespace {
@@ -555,7 +587,9 @@ int fused_rows_per_cta(int total_rows, int M, int K) {
     int rows = ((total_rows + sms - 1) / sms + 31) / 32 * 32;
     if (rows < 32) rows = 32;
     if (rows > 192) rows = 192;
-    if (M > 2 || fused::smem_bytes(M, K, rows) > 224 * 1024) return 0;
+    if (M > 2) return 0;
+    while (rows > 32 && fused::smem_bytes(M, K, rows) > 224 * 1024) rows -= 32;  // large K: fewer rows, a second wave
+    if (fused::smem_bytes(M, K, rows) > 224 * 1024) return 0;
     return rows;
 }
 
@@ -603,6 +637,113 @@ int fused_launch(fused::Args a, int param_dtype, cudaStream_t s, int* ctas_per_p
     });
 }
 
+int allreduce(const onebit_decoder* D, float* data, int64_t count, cudaStream_t s) {
+    if (D->tp <= 1) return ONEBIT_OK;
+    if (!D->allreduce) return fail(ONEBIT_ERR_INVALID_ARGUMENT, "tensor-parallel decoder without an all-reduce callback");
+    const int rc = D->allreduce(D->allreduce_user, data, count, s);
+    return rc == 0 ? ONEBIT_OK : fail(ONEBIT_ERR_CUDA, "all-reduce callback failed with code " + std::to_string(rc));
+}
+
+// The fused-stage layer loop (5 launches per layer; + 4 small collectives per layer under tensor parallelism:
+// (sum,sumsq) of q/k/v, partial sums of o_proj, (sum,sumsq) of gate/up, partial sums of down_proj — SURVEY.md §8e).
+// Returns false through *ok if this shape cannot use the fused stages.
+int run_fused_layers(onebit_decoder* D, int M, cudaStream_t s, bool with_attention, bool first_is_embed, int* launches,
+                     int* cur_io, int* nc_d_io, bool* ok) {
+    const onebit_decoder_config& C = D->cfg;
+    const int H = C.hidden_size, I = C.intermediate_size, pd = C.param_dtype, B = C.max_batch;
+    const int Hl = D->Hl, Hk = D->Hk, Il = D->Il, Ik = D->Ik, tp = D->tp;
+    const int uH = H / imma::kUnitCols, uHk = Hk / imma::kUnitCols, uIk = Ik / imma::kUnitCols;
+    const int cHl = (Hl + imma::kRows - 1) / imma::kRows, cIl = (Il + imma::kRows - 1) / imma::kRows;
+    const int rq = fused_rows_per_cta(3 * Hl, M, H), ro = fused_rows_per_cta(H, M, Hk);
+    const int rg = fused_rows_per_cta(2 * Il, M, H), rd = fused_rows_per_cta(H, M, Ik);
+    *ok = fused_enabled() && rq && ro && rg && rd;
+    if (!*ok) return ONEBIT_OK;
+    int cur = *cur_io, nc_d = *nc_d_io, rc;
+    for (int l = 0; l < C.num_layers; ++l) {
+        const onebit_layer_params& P = D->layers[l];
+        int nc_q = 0, nc_o = 0, nc_g = 0;
+        // ---- stage 1: (embed | resid + LN(down)) -> RMSNorm -> q,k,v (column-parallel: local rows)
+        fused::Args f = {};
+        f.nprob = 3; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rq;
+        f.mode = (l == 0 && first_is_embed) ? fused::EMBED_NORM : fused::RESID_NORM;
+        f.t_a = D->t_d; f.stats_a = D->st_d; f.ncta_a = nc_d; f.stats_from_data = tp > 1;
+        f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1];
+        f.embed = D->embed; f.ids = D->ids; f.ln_w = P.input_layernorm; f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
+        const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
+        for (int i = 0; i < 3; ++i) {
+            f.p[i].w = reinterpret_cast<const uint8_t*>(qkv[i]->weight); f.p[i].g = qkv[i]->weight_scale;
+            f.p[i].h = qkv[i]->input_factor; f.p[i].t = D->t_qkv + (size_t)i * B * Hl;
+            f.p[i].stats = D->st_qkv + (size_t)i * cHl * B * 2; f.p[i].n_rows = Hl; f.p[i].ld_t = Hl;
+        }
+        rc = fused_launch(f, pd, s, &nc_q); if (rc) return rc; ++*launches;
+        cur ^= 1;
+        const float* sq = f.p[0].stats; const float* sk = f.p[1].stats; const float* sv = f.p[2].stats;
+        int nc_attn = nc_q;
+        if (tp > 1) {  // LayerNorm spans the full N: all-reduce 3 x (sum, sumsq) per token
+            rc = launch_pdl(reduce_stats_kernel, dim3(3 * M), dim3(256), 0, s, (const float*)D->st_qkv, cHl * B * 2, nc_q, M,
+                            D->red_qkv);
+            if (rc) return rc; ++*launches;
+            rc = allreduce(D, D->red_qkv, (int64_t)3 * M * 2, s); if (rc) return rc;
+            sq = D->red_qkv; sk = D->red_qkv + (size_t)M * 2; sv = D->red_qkv + (size_t)2 * M * 2; nc_attn = 1;
+        }
+        // ---- stage 2: attention over the local heads
+        if (with_attention) {
+            AttnArgs at = {};
+            at.t_q = f.p[0].t; at.t_k = f.p[1].t; at.t_v = f.p[2].t;
+            at.stats_q = sq; at.stats_k = sk; at.stats_v = sv; at.ncta = nc_attn;
+            at.M = M; at.H = Hl; at.n_ln = H; at.out_ld = Hk; at.n_heads = D->heads_l; at.max_seq = C.max_seq_len;
+            at.pos = D->pos; at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
+            const size_t layer_cache = (size_t)B * D->heads_l * C.max_seq_len * kHeadDim;
+            at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
+            at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = std::min(C.max_seq_len, 384);
+            rc = launch_pdl(attn_kernel, dim3(M, D->heads_l), dim3(kHeadDim), attn_smem_bytes(C.max_seq_len), s, at);
+            if (rc) return rc; ++*launches;
+        }
+        // ---- stage 3: attention output -> o_proj (row-parallel: local K slice, zero-padded to a multiple of 256)
+        f = {};
+        f.nprob = 1; f.M = M; f.K = Hk; f.units = uHk; f.rows_per_cta = ro; f.mode = fused::PLAIN; f.x_plain = D->attn_out;
+        f.p[0].w = reinterpret_cast<const uint8_t*>(P.o.weight); f.p[0].g = P.o.weight_scale; f.p[0].h = P.o.input_factor;
+        f.p[0].t = D->t_o; f.p[0].stats = D->st_o; f.p[0].n_rows = H; f.p[0].ld_t = H;
+        rc = fused_launch(f, pd, s, &nc_o); if (rc) return rc; ++*launches;
+        rc = allreduce(D, D->t_o, (int64_t)M * H, s); if (rc) return rc;  // partial sums of the K shards
+        // ---- stage 4: resid + LN(o) -> RMSNorm -> gate, up (column-parallel)
+        f = {};
+        f.nprob = 2; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rg; f.mode = fused::RESID_NORM;
+        f.t_a = D->t_o; f.stats_a = D->st_o; f.ncta_a = nc_o; f.stats_from_data = tp > 1;
+        f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1]; f.ln_w = P.post_attention_layernorm;
+        f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
+        const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
+        for (int i = 0; i < 2; ++i) {
+            f.p[i].w = reinterpret_cast<const uint8_t*>(gu[i]->weight); f.p[i].g = gu[i]->weight_scale;
+            f.p[i].h = gu[i]->input_factor; f.p[i].t = D->t_gu + (size_t)i * B * Ik;
+            f.p[i].stats = D->st_gu + (size_t)i * cIl * B * 2; f.p[i].n_rows = Il; f.p[i].ld_t = Ik;
+        }
+        rc = fused_launch(f, pd, s, &nc_g); if (rc) return rc; ++*launches;
+        cur ^= 1;
+        const float* sg = f.p[0].stats; const float* su = f.p[1].stats;
+        int nc_gu = nc_g;
+        if (tp > 1) {
+            rc = launch_pdl(reduce_stats_kernel, dim3(2 * M), dim3(256), 0, s, (const float*)D->st_gu, cIl * B * 2, nc_g, M,
+                            D->red_gu);
+            if (rc) return rc; ++*launches;
+            rc = allreduce(D, D->red_gu, (int64_t)2 * M * 2, s); if (rc) return rc;
+            sg = D->red_gu; su = D->red_gu + (size_t)M * 2; nc_gu = 1;
+        }
+        // ---- stage 5: silu(LN(gate)) * LN(up) -> down_proj (row-parallel)
+        fused::Args f5 = {};
+        f5.nprob = 1; f5.M = M; f5.K = Ik; f5.units = uIk; f5.rows_per_cta = rd; f5.mode = fused::SILU_MUL;
+        f5.t_a = f.p[0].t; f5.stats_a = sg; f5.ncta_a = nc_gu; f5.t_b = f.p[1].t; f5.stats_b = su; f5.ncta_b = nc_gu;
+        f5.ln_eps = C.ln_eps; f5.n_ln = I;
+        f5.p[0].w = reinterpret_cast<const uint8_t*>(P.down.weight); f5.p[0].g = P.down.weight_scale;
+        f5.p[0].h = P.down.input_factor; f5.p[0].t = D->t_d; f5.p[0].stats = D->st_d; f5.p[0].n_rows = H; f5.p[0].ld_t = H;
+        rc = fused_launch(f5, pd, s, &nc_d); if (rc) return rc; ++*launches;
+        rc = allreduce(D, D->t_d, (int64_t)M * H, s); if (rc) return rc;
+    }
+    *cur_io = cur;
+    *nc_d_io = nc_d;
+    return ONEBIT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -628,7 +769,11 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     ONEBIT_REQUIRE(H % imma::kUnitCols == 0 && I % imma::kUnitCols == 0 && I <= 14336 && H <= 14336,
                    "decoder_create: hidden/intermediate size must be multiples of 256 and <= 14336");
     ONEBIT_REQUIRE(B >= 1 && B <= imma::kMaxTokens, "decoder_create: the fused step serves batch 1..8 per replica");
-    ONEBIT_REQUIRE(cfg->tp_size <= 1, "decoder_create: tensor-parallel shards are not wired in this build");
+    const int tp = cfg->tp_size > 1 ? cfg->tp_size : 1;
+    ONEBIT_REQUIRE(cfg->num_heads % tp == 0 && I % tp == 0 && (I / tp) % 8 == 0,
+                   "decoder_create: heads and intermediate size must divide by tp_size");
+    ONEBIT_REQUIRE(tp == 1 || allreduce != nullptr, "decoder_create: tp_size > 1 needs an all-reduce callback");
+    ONEBIT_REQUIRE(tp == 1 || (cfg->tp_rank >= 0 && cfg->tp_rank < tp), "decoder_create: bad tp_rank");
     ONEBIT_REQUIRE(H % 8 == 0, "decoder_create: hidden must be a multiple of 8");
     onebit_decoder* D = new (std::nothrow) onebit_decoder();
     ONEBIT_REQUIRE(D, "decoder_create: out of host memory");
@@ -641,6 +786,12 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     D->rope_sin = rope_sin;
     D->allreduce = allreduce;
     D->allreduce_user = allreduce_user;
+    D->tp = tp;
+    D->heads_l = cfg->num_heads / tp;
+    D->Hl = H / tp;
+    D->Il = I / tp;
+    D->Hk = (D->Hl + imma::kUnitCols - 1) / imma::kUnitCols * imma::kUnitCols;  // K of the o_proj shard (zero padded)
+    D->Ik = (D->Il + imma::kUnitCols - 1) / imma::kUnitCols * imma::kUnitCols;  // K of the down_proj shard
 
     const int uH = H / imma::kUnitCols, uI = I / imma::kUnitCols;
     const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
@@ -656,9 +807,10 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     const size_t o_dgu = take((size_t)2 * B * uH * imma::kUnitBytes), o_dd = take((size_t)B * uI * imma::kUnitBytes);
     const size_t o_qqkv = take(3 * B * sizeof(imma::QMeta)), o_qo = take(B * sizeof(imma::QMeta));
     const size_t o_qgu = take(2 * B * sizeof(imma::QMeta)), o_qd = take(B * sizeof(imma::QMeta));
-    const size_t cache_elems = (size_t)L * B * cfg->num_heads * cfg->max_seq_len * kHeadDim;
+    const size_t cache_elems = (size_t)L * B * D->heads_l * cfg->max_seq_len * kHeadDim;
     const size_t o_kc = take(cache_elems * 2), o_vc = take(cache_elems * 2);
     const size_t o_x16 = take((size_t)B * H * 2), o_ids = take(B * 8), o_ids2 = take(B * 8), o_pos = take(B * 4);
+    const size_t o_rq = take((size_t)3 * B * 2 * 4), o_rg = take((size_t)2 * B * 2 * 4);
     cudaError_t e = cudaMalloc(&D->arena, off);
     if (e != cudaSuccess) {
         delete D;
@@ -675,6 +827,7 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     D->qm_gu = (imma::QMeta*)(a + o_qgu); D->qm_d = (imma::QMeta*)(a + o_qd);
     D->kcache = (__half*)(a + o_kc); D->vcache = (__half*)(a + o_vc); D->x_f16 = (__half*)(a + o_x16);
     D->ids = (long long*)(a + o_ids); D->ids_stage = (long long*)(a + o_ids2); D->pos = (int*)(a + o_pos);
+    D->red_qkv = (float*)(a + o_rq); D->red_gu = (float*)(a + o_rg);
     *out = D;
     return ONEBIT_OK;
 }
@@ -707,71 +860,20 @@ int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_
         if (rc) return rc;
         ++launches;
     }
-    int cur = 0;  // residual ping-pong index holding the current stream
-    const int rq = fused_enabled() ? fused_rows_per_cta(3 * H, M, H) : 0;
-    const int ro = fused_enabled() ? fused_rows_per_cta(H, M, H) : 0;
-    const int rg = fused_enabled() ? fused_rows_per_cta(2 * I, M, H) : 0;
-    const int rd = fused_enabled() ? fused_rows_per_cta(H, M, I) : 0;
-    const bool use_fused = rq && ro && rg && rd;
-    int nc_d = cH;  // CTAs that wrote the (sum, sumsq) partials of the last down_proj
-    for (int l = 0; use_fused && l < C.num_layers; ++l) {
-        const onebit_layer_params& P = D->layers[l];
-        int nc_q = 0, nc_o = 0, nc_g = 0;
-        // ---- stage 1: (embed | resid + LN(down)) -> RMSNorm -> q,k,v
-        fused::Args f = {};
-        f.nprob = 3; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rq;
-        f.mode = l == 0 ? fused::EMBED_NORM : fused::RESID_NORM;
-        f.t_a = D->t_d; f.stats_a = D->st_d; f.ncta_a = nc_d;
-        f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1];
-        f.embed = D->embed; f.ids = D->ids; f.ln_w = P.input_layernorm; f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
-        const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
-        for (int i = 0; i < 3; ++i) {
-            f.p[i].w = reinterpret_cast<const uint8_t*>(qkv[i]->weight); f.p[i].g = qkv[i]->weight_scale;
-            f.p[i].h = qkv[i]->input_factor; f.p[i].t = D->t_qkv + (size_t)i * C.max_batch * H;
-            f.p[i].stats = D->st_qkv + (size_t)i * cH * C.max_batch * 2; f.p[i].n_rows = H;
-        }
-        rc = fused_launch(f, pd, s, &nc_q); if (rc) return rc; ++launches;
-        cur ^= 1;
-        // ---- stage 2: attention
-        AttnArgs at = {};
-        at.t_q = f.p[0].t; at.t_k = f.p[1].t; at.t_v = f.p[2].t;
-        at.stats_q = f.p[0].stats; at.stats_k = f.p[1].stats; at.stats_v = f.p[2].stats; at.ncta = nc_q;
-        at.M = M; at.H = H; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len; at.pos = D->pos;
-        at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
-        const size_t layer_cache = (size_t)C.max_batch * C.num_heads * C.max_seq_len * kHeadDim;
-        at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
-        at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = std::min(C.max_seq_len, 384);
-        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), attn_smem_bytes(C.max_seq_len), s, at);
-        if (rc) return rc; ++launches;
-        // ---- stage 3: attention output -> o_proj
-        f = {};
-        f.nprob = 1; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = ro; f.mode = fused::PLAIN; f.x_plain = D->attn_out;
-        f.p[0].w = reinterpret_cast<const uint8_t*>(P.o.weight); f.p[0].g = P.o.weight_scale; f.p[0].h = P.o.input_factor;
-        f.p[0].t = D->t_o; f.p[0].stats = D->st_o; f.p[0].n_rows = H;
-        rc = fused_launch(f, pd, s, &nc_o); if (rc) return rc; ++launches;
-        // ---- stage 4: resid + LN(o) -> RMSNorm -> gate, up
-        f = {};
-        f.nprob = 2; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rg; f.mode = fused::RESID_NORM;
-        f.t_a = D->t_o; f.stats_a = D->st_o; f.ncta_a = nc_o;
-        f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1]; f.ln_w = P.post_attention_layernorm;
-        f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
-        const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
-        for (int i = 0; i < 2; ++i) {
-            f.p[i].w = reinterpret_cast<const uint8_t*>(gu[i]->weight); f.p[i].g = gu[i]->weight_scale;
-            f.p[i].h = gu[i]->input_factor; f.p[i].t = D->t_gu + (size_t)i * C.max_batch * I;
-            f.p[i].stats = D->st_gu + (size_t)i * cI * C.max_batch * 2; f.p[i].n_rows = I;
-        }
-        rc = fused_launch(f, pd, s, &nc_g); if (rc) return rc; ++launches;
-        cur ^= 1;
-        // ---- stage 5: silu(LN(gate)) * LN(up) -> down_proj
-        fused::Args f5 = {};
-        f5.nprob = 1; f5.M = M; f5.K = I; f5.units = uI; f5.rows_per_cta = rd; f5.mode = fused::SILU_MUL;
-        f5.t_a = f.p[0].t; f5.stats_a = f.p[0].stats; f5.ncta_a = nc_g;
-        f5.t_b = f.p[1].t; f5.stats_b = f.p[1].stats; f5.ncta_b = nc_g; f5.ln_eps = C.ln_eps;
-        f5.p[0].w = reinterpret_cast<const uint8_t*>(P.down.weight); f5.p[0].g = P.down.weight_scale;
-        f5.p[0].h = P.down.input_factor; f5.p[0].t = D->t_d; f5.p[0].stats = D->st_d; f5.p[0].n_rows = H;
-        rc = fused_launch(f5, pd, s, &nc_d); if (rc) return rc; ++launches;
+    {   // the stand-alone GEMV keeps every token's digits of the widest layer in shared memory
+        const int nt = M <= 2 ? 1 : (M <= 4 ? 2 : 4);
+        if (imma::gemv_smem_bytes(M, std::max(uH, uI), nt) > 224 * 1024)
+            return fail(ONEBIT_ERR_INVALID_ARGUMENT,
+                        "decoder_step: batch " + std::to_string(M) + " does not fit the decode GEMV for this model width "
+                        "(LLaMA-7B: up to 4, LLaMA2-13B: up to 3 sequences per replica; use more replicas)");
     }
+    int cur = 0;  // residual ping-pong index holding the current stream
+    int nc_d = cH;  // CTAs that wrote the (sum, sumsq) partials of the last down_proj
+    bool use_fused = false;
+    rc = run_fused_layers(D, M, s, /*with_attention=*/true, /*first_is_embed=*/true, &launches, &cur, &nc_d, &use_fused);
+    if (rc) return rc;
+    if (!use_fused && D->tp > 1)
+        return fail(ONEBIT_ERR_INVALID_ARGUMENT, "tensor-parallel decode needs the fused stages (batch <= 2, ONEBIT_FUSED != 0)");
     for (int l = 0; !use_fused && l < C.num_layers; ++l) {
         const onebit_layer_params& P = D->layers[l];
         // ---- glue 1: (embed | resid + LN(down of previous layer)) -> RMSNorm -> q/k/v digits
@@ -801,9 +903,9 @@ int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_
         AttnArgs at = {};
         at.t_q = a.p[0].t; at.t_k = a.p[1].t; at.t_v = a.p[2].t;
         at.stats_q = a.p[0].stats; at.stats_k = a.p[1].stats; at.stats_v = a.p[2].stats; at.ncta = cH;
-        at.M = M; at.H = H; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len; at.pos = D->pos;
+        at.M = M; at.H = H; at.n_ln = H; at.out_ld = H; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len; at.pos = D->pos;
         at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
-        const size_t layer_cache = (size_t)C.max_batch * C.num_heads * C.max_seq_len * kHeadDim;
+        const size_t layer_cache = (size_t)C.max_batch * D->heads_l * C.max_seq_len * kHeadDim;
         at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
         at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = std::min(C.max_seq_len, 384);
         rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), attn_smem_bytes(C.max_seq_len), s, at);
@@ -860,7 +962,7 @@ int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_
     // ---- final: resid + LN(down) -> RMSNorm(final) -> fp16 x -> lm_head -> argmax
     GlueArgs g = {};
     g.mode = GLUE_RESID_NORM; g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1;
-    g.t_a = D->t_d; g.stats_a = D->st_d; g.ncta_a = use_fused ? nc_d : cH;
+    g.t_a = D->t_d; g.stats_a = D->st_d; g.ncta_a = use_fused ? nc_d : cH; g.stats_from_data = D->tp > 1;
     g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = D->final_norm;
     g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps; g.x_f16 = D->x_f16;
     rc = glue_launch(D, g, s); if (rc) return rc; ++launches;
@@ -896,51 +998,12 @@ int onebit_decoder_gemv_only(onebit_decoder* D, int batch, void* stream) {
     const int uH = H / imma::kUnitCols, uI = I / imma::kUnitCols;
     const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
     const size_t dgH = (size_t)C.max_batch * uH * imma::kUnitBytes;
-    const int rq = fused_enabled() ? fused_rows_per_cta(3 * H, M, H) : 0, ro = fused_enabled() ? fused_rows_per_cta(H, M, H) : 0;
-    const int rg = fused_enabled() ? fused_rows_per_cta(2 * I, M, H) : 0, rd = fused_enabled() ? fused_rows_per_cta(H, M, I) : 0;
-    if (rq && ro && rg && rd) {  // the fused glue+GEMV stages (what the step really runs), attention skipped
-        int nc_d = cH, cur = 0;
-        for (int l = 0; l < C.num_layers; ++l) {
-            const onebit_layer_params& P = D->layers[l];
-            int nc_q = 0, nc_o = 0, nc_g = 0, rc;
-            fused::Args f = {};
-            f.nprob = 3; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rq; f.mode = fused::RESID_NORM;
-            f.t_a = D->t_d; f.stats_a = D->st_d; f.ncta_a = nc_d; f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1];
-            f.ln_w = P.input_layernorm; f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
-            const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
-            for (int i = 0; i < 3; ++i) {
-                f.p[i].w = reinterpret_cast<const uint8_t*>(qkv[i]->weight); f.p[i].g = qkv[i]->weight_scale;
-                f.p[i].h = qkv[i]->input_factor; f.p[i].t = D->t_qkv + (size_t)i * C.max_batch * H;
-                f.p[i].stats = D->st_qkv + (size_t)i * cH * C.max_batch * 2; f.p[i].n_rows = H;
-            }
-            rc = fused_launch(f, pd, s, &nc_q); if (rc) return rc;
-            cur ^= 1;
-            f = {};
-            f.nprob = 1; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = ro; f.mode = fused::PLAIN; f.x_plain = D->attn_out;
-            f.p[0].w = reinterpret_cast<const uint8_t*>(P.o.weight); f.p[0].g = P.o.weight_scale; f.p[0].h = P.o.input_factor;
-            f.p[0].t = D->t_o; f.p[0].stats = D->st_o; f.p[0].n_rows = H;
-            rc = fused_launch(f, pd, s, &nc_o); if (rc) return rc;
-            f = {};
-            f.nprob = 2; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rg; f.mode = fused::RESID_NORM;
-            f.t_a = D->t_o; f.stats_a = D->st_o; f.ncta_a = nc_o; f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1];
-            f.ln_w = P.post_attention_layernorm; f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
-            const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
-            for (int i = 0; i < 2; ++i) {
-                f.p[i].w = reinterpret_cast<const uint8_t*>(gu[i]->weight); f.p[i].g = gu[i]->weight_scale;
-                f.p[i].h = gu[i]->input_factor; f.p[i].t = D->t_gu + (size_t)i * C.max_batch * I;
-                f.p[i].stats = D->st_gu + (size_t)i * cI * C.max_batch * 2; f.p[i].n_rows = I;
-            }
-            rc = fused_launch(f, pd, s, &nc_g); if (rc) return rc;
-            cur ^= 1;
-            fused::Args f5 = {};
-            f5.nprob = 1; f5.M = M; f5.K = I; f5.units = uI; f5.rows_per_cta = rd; f5.mode = fused::SILU_MUL;
-            f5.t_a = f.p[0].t; f5.stats_a = f.p[0].stats; f5.ncta_a = nc_g; f5.t_b = f.p[1].t; f5.stats_b = f.p[1].stats;
-            f5.ncta_b = nc_g; f5.ln_eps = C.ln_eps;
-            f5.p[0].w = reinterpret_cast<const uint8_t*>(P.down.weight); f5.p[0].g = P.down.weight_scale;
-            f5.p[0].h = P.down.input_factor; f5.p[0].t = D->t_d; f5.p[0].stats = D->st_d; f5.p[0].n_rows = H;
-            rc = fused_launch(f5, pd, s, &nc_d); if (rc) return rc;
-        }
-        return ONEBIT_OK;
+    {
+        int launches = 0, cur = 0, nc_d = cH;
+        bool used = false;
+        int rc = run_fused_layers(D, M, s, /*with_attention=*/false, /*first_is_embed=*/false, &launches, &cur, &nc_d, &used);
+        if (rc) return rc;
+        if (used) return ONEBIT_OK;
     }
     for (int l = 0; l < C.num_layers; ++l) {
         const onebit_layer_params& P = D->layers[l];

@@ -36,6 +36,7 @@ struct Problem {
     float* t;          // [M][n_rows] fp32 out (= g * S @ (h*x))
     float* stats;      // [ctas of this problem][M][2]
     int n_rows;
+    int ld_t;          // row stride of t (>= n_rows; tensor-parallel shards pad it to the consumer's K)
     int cta_begin;
 };
 
@@ -50,6 +51,8 @@ struct Args {
     const void* ln_w;                                     // RMSNorm weight (TP)
     const float* x_plain;                                 // PLAIN
     float ln_eps, rms_eps;
+    int n_ln;             // rows of the producer's FULL layer (LayerNorm denominator); 0 = K
+    int stats_from_data;  // RESID_NORM: t_a was all-reduced across ranks -> take (sum, sumsq) from the data itself
 };
 
 inline size_t smem_bytes(int M, int K, int rows_per_cta) {
@@ -241,13 +244,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemv_kernel(const __grid_co
             }
         }
         // (the partial-sum loads come after the big loads in program order: their fp64 conversion stalls the warp)
-        if (A.mode == RESID_NORM || A.mode == SILU_MUL) stat_partials(A.stats_a, A.ncta_a, M, m, st[0], st[1]);
+        if ((A.mode == RESID_NORM && !A.stats_from_data) || A.mode == SILU_MUL) stat_partials(A.stats_a, A.ncta_a, M, m, st[0], st[1]);
         if (A.mode == SILU_MUL) stat_partials(A.stats_b, A.ncta_b, M, m, st[2], st[3]);
         float mean_a = 0.f, rstd_a = 1.f, mean_b = 0.f, rstd_b = 1.f;
         if (A.mode == RESID_NORM || A.mode == SILU_MUL) {
+            if (A.mode == RESID_NORM && A.stats_from_data) {  // tensor parallel: statistics of the reduced vector
+                st[0] = st[1] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NV4; ++i)
+                    if (i * kThreads + tid < K4) {
+                        st[0] += (double)((va[i].x + va[i].y) + (va[i].z + va[i].w));
+                        st[1] += (double)((va[i].x * va[i].x + va[i].y * va[i].y) + (va[i].z * va[i].z + va[i].w * va[i].w));
+                    }
+            }
             block_sum<4>(st, shd);
-            finish_ln(st[0], st[1], K, A.ln_eps, mean_a, rstd_a);
-            if (A.mode == SILU_MUL) finish_ln(st[2], st[3], K, A.ln_eps, mean_b, rstd_b);
+            const int nln = A.n_ln > 0 ? A.n_ln : K;
+            finish_ln(st[0], st[1], nln, A.ln_eps, mean_a, rstd_a);
+            if (A.mode == SILU_MUL) finish_ln(st[2], st[3], nln, A.ln_eps, mean_b, rstd_b);
         }
         TR(2);
         float am = 0.f;
@@ -411,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemv_kernel(const __grid_co
             }
             const long long V = (((long long)a.w * 256 + a.z) * 256 + a.y) * 256 + a.x;  // 128 * sum_{bit=1} q
             const float val = (float)((double)(s_qtot[m] - 2 * (V >> 7)) * s_invd[m]) * to_f32(graw);
-            P.t[(size_t)m * P.n_rows + row0 + r] = val;
+            P.t[(size_t)m * P.ld_t + row0 + r] = val;
             st[0] = (double)val;
             st[1] = (double)val * (double)val;
         }

@@ -1,0 +1,50 @@
+"""Tensor-parallel decode check (run under torchrun on >= 2 GPUs):
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/tp_check.py
+1) tiny model vs the reference golden logits with tp = world size (eager and CUDA-graphed);
+2) LLaMA-7B-shaped timing of the TP decode step (random weights)."""
+import json, os, sys, time
+from pathlib import Path
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from onebit_b200 import BitLlamaDecoderB200, LLAMA_7B, synthetic_state_dict
+from oracle import oracle
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=dev)
+z = np.load(Path(__file__).resolve().parent.parent / "tests/golden/tiny_model.npz")
+cfg = {k: v for k, v in zip(z["config_keys"], z["config_vals"])}
+config = {k: (float(cfg[k]) if k in ("rms_norm_eps", "rope_theta") else int(cfg[k])) for k in
+          ("hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "vocab_size", "rms_norm_eps", "rope_theta")}
+sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+ids = torch.from_numpy(z["input_ids"])[:, :24]
+res = {}
+for graph in (False, True):
+    dec = BitLlamaDecoderB200(config, sd, device=dev, max_seq_len=64, max_batch=2, param_dtype=torch.float32,
+                              use_graph=graph, tp_group=dist.group.WORLD)
+    logits = dec.forward_tokens(ids).cpu().numpy()
+    res["graph" if graph else "eager"] = oracle.rel_l2(logits, z["logits"][:, :24])
+    dec.close()
+ok = all(v < 2e-3 for v in res.values())
+# timing at LLaMA-7B widths
+cfg7 = dict(LLAMA_7B)
+dec = BitLlamaDecoderB200(cfg7, synthetic_state_dict(cfg7, seed=0), device=dev, max_seq_len=256, max_batch=1,
+                          tp_group=dist.group.WORLD)
+dec.reset(torch.tensor([5]))
+for _ in range(8):
+    dec.step()
+torch.cuda.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(64):
+    dec.step()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 64
+if rank == 0:
+    print(json.dumps({"tp": world, "tiny_model_logits_rel_l2": res, "parity_ok": ok, "llama7b_tp_ms_per_step": ms,
+                      "llama7b_tp_tok_s": 1e3 / ms, "launches_per_step": dec.launches_per_step()}), flush=True)
+dist.barrier(); dist.destroy_process_group()
+sys.exit(0 if ok else 1)
