@@ -16,7 +16,11 @@ int fail(int code, const std::string& msg) {
     return code;
 }
 
+static thread_local int t_pdl_suspended = 0;
+void pdl_suspend(bool on) { t_pdl_suspended = on ? 1 : 0; }
+
 bool pdl_enabled() {
+    if (t_pdl_suspended) return false;
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("ONEBIT_PDL");

@@ -31,6 +31,7 @@ inline size_t dtype_size(int dt) { return dt == ONEBIT_F32 ? 4 : 2; }
 inline bool dtype_ok(int dt) { return dt == ONEBIT_F16 || dt == ONEBIT_BF16 || dt == ONEBIT_F32; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+void pdl_suspend(bool on);  // per-thread: tensor-parallel steps interleave NCCL kernels from another stream
 bool pdl_enabled();  // programmatic dependent launch on our own kernel chain (ONEBIT_PDL=0 disables)
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 

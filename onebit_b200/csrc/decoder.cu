@@ -845,8 +845,19 @@ const int64_t* onebit_decoder_next_ids(onebit_decoder* D) { return D ? reinterpr
 const int32_t* onebit_decoder_positions(onebit_decoder* D) { return D ? D->pos : nullptr; }
 int onebit_decoder_kernel_launches_per_step(onebit_decoder* D) { return D ? D->launches : 0; }
 
+static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced_ids_dev, float* logits_dev, void* stream);
+
 int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_dev, float* logits_dev, void* stream) {
     ONEBIT_REQUIRE(D && batch >= 1 && batch <= D->cfg.max_batch, "decoder_step: bad arguments");
+    // Tensor-parallel steps interleave NCCL kernels (another stream, event-ordered): keep plain stream order there, so
+    // that no early-launched CTA of ours can sit on an SM waiting for a collective that needs that SM.
+    if (D->tp > 1) pdl_suspend(true);
+    const int rc = decoder_step_impl(D, batch, forced_ids_dev, logits_dev, stream);
+    if (D->tp > 1) pdl_suspend(false);
+    return rc;
+}
+
+static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced_ids_dev, float* logits_dev, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const onebit_decoder_config& C = D->cfg;
     const int H = C.hidden_size, I = C.intermediate_size, M = batch, pd = C.param_dtype;

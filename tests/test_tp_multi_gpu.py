@@ -1,0 +1,24 @@
+"""Tensor-parallel decode on real GPUs (needs >= 2 devices; skipped otherwise — the single-GPU round-end run skips it).
+Launches tools/tp_check.py under torchrun with a hard timeout so that a communication problem cannot hang the suite.
+
+Status (round 1): the host-side sharding and the collective plumbing are verified on CPU (tests/test_tp_gloo_cpu.py);
+the one 2-GPU attempt of this check did not finish inside its time limit and the round's GPU budget ended before it
+could be debugged, so the tensor-parallel decode path is NOT yet verified on hardware."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_tp2_tiny_model_matches_reference_logits():
+    cmd = ["timeout", "240", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29571", str(ROOT / "tools" / "tp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(ROOT))
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert '"parity_ok": true' in r.stdout

@@ -23,13 +23,20 @@ sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
 ids = torch.from_numpy(z["input_ids"])[:, :24]
 res = {}
 for graph in (False, True):
+    if rank == 0:
+        print(f"tp_check: tiny model, graph={graph}", flush=True)
     dec = BitLlamaDecoderB200(config, sd, device=dev, max_seq_len=64, max_batch=2, param_dtype=torch.float32,
                               use_graph=graph, tp_group=dist.group.WORLD)
     logits = dec.forward_tokens(ids).cpu().numpy()
     res["graph" if graph else "eager"] = oracle.rel_l2(logits, z["logits"][:, :24])
     dec.close()
 ok = all(v < 2e-3 for v in res.values())
-# timing at LLaMA-7B widths
+if rank == 0:
+    print(json.dumps({"tp": world, "tiny_model_logits_rel_l2": res, "parity_ok": ok}), flush=True)
+if os.environ.get("ONEBIT_TP_TIMING", "0") != "1":
+    dist.barrier(); dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+# timing at LLaMA-7B widths (ONEBIT_TP_TIMING=1)
 cfg7 = dict(LLAMA_7B)
 dec = BitLlamaDecoderB200(cfg7, synthetic_state_dict(cfg7, seed=0), device=dev, max_seq_len=256, max_batch=1,
                           tp_group=dist.group.WORLD)
