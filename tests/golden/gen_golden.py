@@ -218,9 +218,19 @@ def gen_model():
     print("tiny_model.npz ppl", ppl.item(), "generated", gen.shape)
 
 
+def gen_rope():
+    """cos/sin caches of the reference's LlamaRotaryEmbedding (modeling_bitllama.py:87-121), head_dim 128."""
+    import_reference_transformers()
+    from transformers.models.bitllama.modeling_bitllama import LlamaRotaryEmbedding
+    rot = LlamaRotaryEmbedding(128, max_position_embeddings=512, base=10000.0)
+    cos, sin = rot(torch.zeros(1, 1, 512, 128), seq_len=512)
+    np.savez_compressed(HERE / "rope_tables.npz", cos=cos.float().numpy(), sin=sin.float().numpy())
+    print("rope_tables.npz", cos.shape)
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
-    which = set(sys.argv[1:]) or {"pack", "forward", "equiv", "model"}
+    which = set(sys.argv[1:]) or {"pack", "forward", "equiv", "model", "rope"}
     bitnet = load_bitnet()
     packer = load_packer()
     if "pack" in which:
@@ -231,3 +241,5 @@ if __name__ == "__main__":
         gen_forward(bitnet)
     if "model" in which:
         gen_model()
+    if "rope" in which:
+        gen_rope()
