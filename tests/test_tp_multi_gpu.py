@@ -2,8 +2,8 @@
 Launches tools/tp_check.py under torchrun with a hard timeout so that a communication problem cannot hang the suite.
 
 Status (round 1): the host-side sharding and the collective plumbing are verified on CPU (tests/test_tp_gloo_cpu.py);
-the one 2-GPU attempt of this check did not finish inside its time limit and the round's GPU budget ended before it
-could be debugged, so the tensor-parallel decode path is NOT yet verified on hardware."""
+two 2-GPU attempts of this check did not finish inside their time limits and the round's GPU budget ended before the
+cause could be isolated, so the tensor-parallel decode path is NOT yet verified on hardware."""
 import subprocess
 import sys
 from pathlib import Path
