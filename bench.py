@@ -26,7 +26,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "llama7b_onebit_decode_tok_s"
+METRIC = "LLaMA-7B-OneBit decode tok/s (greedy, batch 1 per GPU)"  # BASELINE.json metric, configs[1]
 UNIT = "tok/s"
 
 
@@ -164,6 +164,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     name, cfg = model_config(args.model)
+    metric = METRIC if (args.model == "7b" and args.batch == 1) else f"{name} decode tok/s (greedy, batch {args.batch} per GPU)"
     B, K, W = args.batch, args.steps, args.warmup
     prompt_len = 16
     sd = synthetic_state_dict(cfg, seed=rank)
@@ -278,7 +279,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "step_level": {"bitlinear_GBs_over_whole_step": bb["per_step"] / (ms / K * 1e-3) / 1e9,
                                "frac": bb["per_step"] / (ms / K * 1e-3) / 1e9 / peak}}
     cpu = cpu_decode_baseline(cfg, B, tokens=3) if world == 1 else None
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
             "data": "synthetic",
             "config": {"workload": f"{name} greedy decode, batch {B} per GPU, {prompt_len}-token prompt then {K} "
