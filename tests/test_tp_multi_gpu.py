@@ -15,6 +15,11 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
+import os
+
+
+@pytest.mark.skipif(os.environ.get("ONEBIT_RUN_TP_TEST", "0") != "1",
+                    reason="tensor-parallel decode is not yet verified on hardware: opt in with ONEBIT_RUN_TP_TEST=1")
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_tp2_tiny_model_matches_reference_logits():
     cmd = ["timeout", "240", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
