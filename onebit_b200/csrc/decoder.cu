@@ -775,6 +775,7 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     ONEBIT_REQUIRE(tp == 1 || allreduce != nullptr, "decoder_create: tp_size > 1 needs an all-reduce callback");
     ONEBIT_REQUIRE(tp == 1 || (cfg->tp_rank >= 0 && cfg->tp_rank < tp), "decoder_create: bad tp_rank");
     ONEBIT_REQUIRE(H % 8 == 0, "decoder_create: hidden must be a multiple of 8");
+    ONEBIT_REQUIRE(cfg->max_seq_len <= 6144, "decoder_create: max_seq_len up to 6144 (attention keeps the score row + 384 cached K/V rows in shared memory)");
     onebit_decoder* D = new (std::nothrow) onebit_decoder();
     ONEBIT_REQUIRE(D, "decoder_create: out of host memory");
     D->cfg = *cfg;
