@@ -178,6 +178,16 @@ ONEBIT_API int onebit_decoder_gemv_only(onebit_decoder* dec, int batch, void* st
 ONEBIT_API const int64_t* onebit_decoder_next_ids(onebit_decoder* dec);  /* device int64 [max_batch] */
 ONEBIT_API const int32_t* onebit_decoder_positions(onebit_decoder* dec); /* device int32 [max_batch] */
 ONEBIT_API int onebit_decoder_kernel_launches_per_step(onebit_decoder* dec);
+/* Persistent single-kernel step (batch <= 2, tp_size == 1; ONEBIT_PERSIST=0 disables): 1 if this decoder uses it. */
+ONEBIT_API int onebit_decoder_is_persistent(onebit_decoder* dec);
+/* Health of the persistent step (synchronous device read): 0 = fine, 1 = an in-kernel exchange timed out,
+ * 2 = a step was asked to decode past max_seq_len (it wrote nothing outside the cache). */
+ONEBIT_API int onebit_decoder_status(onebit_decoder* dec, int* code);
+/* Device time stamps (ns, %globaltimer) CTA 0 of the persistent step records at every stage boundary of the LAST
+ * step: [0] kernel start, then per layer l 16 slots at 16*(1+l): [0] layer start, [1] q/k/v done, [2] attention done,
+ * [3] o_proj + gate/up inputs done, [4] gate/up done, [5] down_proj done; then at 16*(1+L): [0] lm_head start,
+ * [1] step end. Returns the number of 64-bit words written (0 when the decoder is not persistent). Synchronous. */
+ONEBIT_API int onebit_decoder_read_trace(onebit_decoder* dec, uint64_t* out, int n);
 ONEBIT_API void onebit_decoder_destroy(onebit_decoder* dec);
 
 #ifdef __cplusplus

@@ -124,6 +124,8 @@ class BitLlamaDecoderB200:
         self._graphs = {}
         self._warmed = set()
         self.batch = 0
+        self._pos_hi = 0  # upper bound of every sequence's position (the C side keeps the same count for eager calls)
+        self.persistent = bool(self.lib.onebit_decoder_is_persistent(self._handle))
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -151,6 +153,10 @@ class BitLlamaDecoderB200:
         b = ids.numel()
         pos = torch.zeros(b, dtype=torch.int32) if positions is None else \
             torch.as_tensor(positions, dtype=torch.int32).reshape(-1).cpu().contiguous()
+        if int(pos.max()) >= self.max_seq_len or int(pos.min()) < 0:
+            raise RuntimeError(f"onebit_b200: positions must lie in [0, max_seq_len={self.max_seq_len})")
+        if int(ids.min()) < 0 or int(ids.max()) >= self.V:
+            raise RuntimeError(f"onebit_b200: token ids must lie in [0, vocab_size={self.V})")
         self.batch = b
         if b not in self._warmed:
             # one eager step per batch size before any graph capture: kernel attributes / lazy module loading
@@ -162,6 +168,7 @@ class BitLlamaDecoderB200:
             torch.cuda.synchronize(self.device)
             self._warmed.add(b)
         self._set_state(ids, pos)
+        self._pos_hi = int(pos.max())
 
     def _enqueue(self, forced: bool):
         rc = self.lib.onebit_decoder_step(self._handle, self.batch, self.forced.data_ptr() if forced else None,
@@ -172,6 +179,10 @@ class BitLlamaDecoderB200:
         """One decode step for all sequences. Feeds `forced_ids` if given, else the previous step's argmax.
         Leaves logits in `self.logits[:batch]` and the next ids on the device (`next_ids()`)."""
         forced = forced_ids is not None
+        if self._pos_hi >= self.max_seq_len:
+            raise RuntimeError(f"onebit_b200: a sequence has reached max_seq_len={self.max_seq_len}; the static KV cache is "
+                               "full (create the decoder with a larger max_seq_len)")
+        self._pos_hi += 1
         if forced:
             self.forced[: self.batch].copy_(forced_ids.reshape(-1), non_blocking=True)  # H2D if the ids are on the host
         with torch.cuda.device(self.device):
@@ -198,6 +209,23 @@ class BitLlamaDecoderB200:
     def launches_per_step(self) -> int:
         return int(self.lib.onebit_decoder_kernel_launches_per_step(self._handle))
 
+    def status(self) -> int:
+        """0 = fine; 1 = an in-kernel exchange of the persistent step timed out; 2 = decode past max_seq_len refused."""
+        code = ctypes.c_int(0)
+        _lib.check(self.lib.onebit_decoder_status(self._handle, ctypes.byref(code)), "onebit_decoder_status")
+        return int(code.value)
+
+    def read_trace(self) -> Optional[np.ndarray]:
+        """Stage time stamps (ns) of the last persistent step: array [L + 2, 16] (see onebit_b200.h), or None."""
+        if not self.persistent:
+            return None
+        n = 16 * (self.L + 2)
+        buf = np.zeros(n, dtype=np.uint64)
+        got = self.lib.onebit_decoder_read_trace(self._handle, buf.ctypes.data, n)
+        if got <= 0:
+            return None
+        return buf.reshape(self.L + 2, 16)
+
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward_tokens(self, input_ids: torch.Tensor) -> torch.Tensor:
@@ -205,6 +233,8 @@ class BitLlamaDecoderB200:
         the quantity BitLlamaForCausalLMInf.forward returns (:1546-1611), computed one position at a time."""
         input_ids = torch.as_tensor(input_ids, dtype=torch.int64)
         b, t = input_ids.shape
+        if t > self.max_seq_len:
+            raise RuntimeError(f"onebit_b200: {t} tokens do not fit max_seq_len={self.max_seq_len}")
         self.reset(input_ids[:, 0])
         out = torch.empty((b, t, self.V), dtype=torch.float32, device=self.device)
         ids_dev = input_ids.to(self.device)
@@ -219,6 +249,8 @@ class BitLlamaDecoderB200:
         [B, T0 + max_new_tokens] like `model.generate`."""
         prompt_ids = torch.as_tensor(prompt_ids, dtype=torch.int64)
         b, t0 = prompt_ids.shape
+        if t0 + max_new_tokens - 1 > self.max_seq_len:
+            raise RuntimeError(f"onebit_b200: prompt {t0} + {max_new_tokens} new tokens do not fit max_seq_len={self.max_seq_len}")
         self.reset(prompt_ids[:, 0])
         ids_dev = prompt_ids.to(self.device)
         for i in range(t0):

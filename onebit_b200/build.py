@@ -25,7 +25,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fP
          "-ccbin", "/usr/bin/g++"]
 # --use_fast_math only affects intrinsics we do not use on the numerics path (no div/exp there);
 # it is dropped for files listed here to keep IEEE division / sqrt in the normalisation kernels.
-PRECISE = {"layernorm.cu", "decoder.cu"}
+PRECISE = {"layernorm.cu", "decoder.cu", "persist_step.cu"}
 
 
 def sources():

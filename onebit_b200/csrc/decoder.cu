@@ -19,6 +19,7 @@
 
 #include "fused_gemv.cuh"
 #include "imma_gemv.cuh"
+#include "persist_step.cuh"
 
 namespace onebit {
 
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     imma::pdl_launch_dependents();
     imma::pdl_wait();
     const int m = blockIdx.x, hd = blockIdx.y, d = threadIdx.x, lane = d & 31, warp = d >> 5;
-    const int pos = A.pos[m], T = pos + 1;
+    const int pos = min(max(A.pos[m], 0), A.max_seq - 1), T = pos + 1;  // host refuses earlier; never index past the cache
     __half* kc = A.kcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
     __half* vc = A.vcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
     // The cached rows 0..pos-1 of this (sequence, head) are contiguous: pull them into shared memory with two bulk
@@ -531,6 +532,11 @@ struct onebit_decoder {
     // tensor-parallel geometry (tp = 1: Hl = Hk = H, Il = Ik = I)
     int tp = 1, Hl = 0, Hk = 0, Il = 0, Ik = 0, heads_l = 0;
     float *red_qkv = nullptr, *red_gu = nullptr;  // [nproj][max_batch][2] all-reduced (sum, sumsq)
+    // persistent single-kernel step (persist_step.cu): batch <= 2, no tensor parallelism
+    PersistState* persist = nullptr;
+    // host-side upper bound of every sequence's position (reset value + steps enqueued): a step that could write past
+    // max_seq_len is refused instead of overrunning the KV cache
+    int pos_hi = 0;
 };
 
 namespace {
@@ -750,6 +756,7 @@ extern "C" {
 
 void onebit_decoder_destroy(onebit_decoder* D) {
     if (!D) return;
+    persist_destroy(D->persist);
     cudaFree(D->arena);
     delete D;
 }
@@ -829,12 +836,27 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     D->kcache = (__half*)(a + o_kc); D->vcache = (__half*)(a + o_vc); D->x_f16 = (__half*)(a + o_x16);
     D->ids = (long long*)(a + o_ids); D->ids_stage = (long long*)(a + o_ids2); D->pos = (int*)(a + o_pos);
     D->red_qkv = (float*)(a + o_rq); D->red_gu = (float*)(a + o_rg);
+    if (persist_supported(*cfg)) {
+        const int rc = persist_create(&D->persist, *cfg, layers, embed_tokens_f16, final_norm, lm_head_f16, rope_cos, rope_sin,
+                                      D->kcache, D->vcache, D->ids, D->pos);
+        if (rc != ONEBIT_OK) {
+            onebit_decoder_destroy(D);
+            return rc;
+        }
+    }
     *out = D;
     return ONEBIT_OK;
 }
 
 int onebit_decoder_reset(onebit_decoder* D, const int64_t* ids_host, const int32_t* pos_host, int batch, void* stream) {
     ONEBIT_REQUIRE(D && ids_host && pos_host && batch >= 1 && batch <= D->cfg.max_batch, "decoder_reset: bad arguments");
+    int hi = 0;
+    for (int b = 0; b < batch; ++b) {
+        ONEBIT_REQUIRE(ids_host[b] >= 0 && ids_host[b] < D->cfg.vocab_size, "decoder_reset: token id outside [0, vocab_size)");
+        ONEBIT_REQUIRE(pos_host[b] >= 0 && pos_host[b] < D->cfg.max_seq_len, "decoder_reset: position outside [0, max_seq_len)");
+        hi = std::max(hi, (int)pos_host[b]);
+    }
+    D->pos_hi = hi;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ONEBIT_CUDA_TRY(cudaMemcpyAsync(D->ids, ids_host, (size_t)batch * 8, cudaMemcpyHostToDevice, s));
     ONEBIT_CUDA_TRY(cudaMemcpyAsync(D->pos, pos_host, (size_t)batch * 4, cudaMemcpyHostToDevice, s));
@@ -850,6 +872,17 @@ static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced
 
 int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_dev, float* logits_dev, void* stream) {
     ONEBIT_REQUIRE(D && batch >= 1 && batch <= D->cfg.max_batch, "decoder_step: bad arguments");
+    // the step writes cache row `pos`: refuse once any sequence may have reached the end of the static KV cache
+    // (callers that replay a captured graph must keep the same count themselves: BitLlamaDecoderB200 does)
+    if (D->pos_hi >= D->cfg.max_seq_len)
+        return fail(ONEBIT_ERR_INVALID_ARGUMENT, "decoder_step: a sequence has reached max_seq_len (" + std::to_string(D->cfg.max_seq_len) +
+                                                     "); create the decoder with a longer cache");
+    D->pos_hi += 1;
+    if (D->persist && batch <= persist::kMaxTok) {
+        D->launches = 1;
+        return persist_step(D->persist, batch, forced_ids_dev ? reinterpret_cast<const long long*>(forced_ids_dev) : D->ids,
+                            logits_dev ? logits_dev : D->logits, static_cast<cudaStream_t>(stream));
+    }
     // Tensor-parallel steps interleave NCCL kernels (another stream, event-ordered): keep plain stream order there, so
     // that no early-launched CTA of ours can sit on an SM waiting for a collective that needs that SM.
     if (D->tp > 1) pdl_suspend(true);
@@ -1065,6 +1098,21 @@ int onebit_decoder_step_host(onebit_decoder* D, int batch, const int64_t* ids_ho
     ONEBIT_CUDA_TRY(cudaStreamSynchronize(s));
     return ONEBIT_OK;
 }
+
+int onebit_decoder_status(onebit_decoder* D, int* code) {
+    ONEBIT_REQUIRE(D && code, "decoder_status: bad arguments");
+    *code = 0;
+    if (D->persist) return persist_abort_flag(D->persist, code);
+    return ONEBIT_OK;
+}
+
+int onebit_decoder_read_trace(onebit_decoder* D, uint64_t* out, int n) {
+    ONEBIT_REQUIRE(D && out && n > 0, "decoder_read_trace: bad arguments");
+    if (!D->persist) return 0;
+    return persist_read_trace(D->persist, reinterpret_cast<unsigned long long*>(out), n);
+}
+
+int onebit_decoder_is_persistent(onebit_decoder* D) { return D && D->persist ? 1 : 0; }
 
 }  // extern "C"
 

@@ -1,0 +1,1379 @@
+// Persistent decode-step kernel (see persist_step.cuh for the design) + its host side.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "imma_gemv.cuh"
+#include "persist_step.cuh"
+
+namespace onebit {
+namespace persist {
+namespace {
+
+using imma::imma16832;
+using imma::mbar_expect_tx;
+using imma::mbar_init;
+using imma::mbar_wait;
+using imma::plane;
+using imma::smem_u32;
+
+// ---------------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
+
+__device__ __forceinline__ uint4 ldv4(const uint32_t* p) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t ldv1(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void stv1(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void stv16(void* p, uint32_t v) { asm volatile("st.volatile.global.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+
+// validity of Lamport words: digit words are invalid while ANY byte still is 0x80; float words while they equal kSentF
+__device__ __forceinline__ uint32_t hz(uint32_t x) {
+    const uint32_t y = x ^ kSentD;
+    return (y - 0x01010101u) & ~y & 0x80808080u;
+}
+__device__ __forceinline__ bool bad_d(const uint4& v) { return (hz(v.x) | hz(v.y) | hz(v.z) | hz(v.w)) != 0u; }
+__device__ __forceinline__ bool bad_f(const uint4& v) { return v.x == kSentF || v.y == kSentF || v.z == kSentF || v.w == kSentF; }
+__device__ __forceinline__ uint32_t fbits(float f) {  // publishable bit pattern of a float
+    const uint32_t b = __float_as_uint(f);
+    return b == kSentF ? 0x7FFFFFFFu : b;
+}
+
+// give-up logic of every polling loop: a protocol bug must end the kernel, not hang the GPU
+__device__ __noinline__ bool spin_giveup_slow(int spins, int* abort_flag) {
+    if (ldv1(reinterpret_cast<const uint32_t*>(abort_flag)) != 0u) return true;
+    if (spins > (1 << 21)) {
+        atomicExch(abort_flag, 1);
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ bool spin_giveup(int& spins, int* abort_flag) {
+    if ((++spins & 1023) != 0) return false;
+    return spin_giveup_slow(spins, abort_flag);
+}
+
+__device__ __forceinline__ size_t dsize(int pdt) { return pdt == ONEBIT_F32 ? 4 : 2; }
+__device__ __noinline__ float ldp(const void* p, int i, int pdt) {  // parameter vector element (runtime dtype)
+    if (pdt == ONEBIT_F16) return __half2float(static_cast<const __half*>(p)[i]);
+    if (pdt == ONEBIT_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+    return static_cast<const float*>(p)[i];
+}
+
+// balanced base-255 digits of v (|v| <= 2^29): four bytes in [-127, 127], sum_d digit_d * 255^d == v
+__device__ __forceinline__ uint32_t digits255(int v) {
+    const uint32_t u = (uint32_t)v + 2114125312u;  // + 127 * (1 + 255 + 255^2 + 255^3)
+    const uint32_t q1 = __umulhi(u, 0x80808081u) >> 7, e0 = u - q1 * 255u;
+    const uint32_t q2 = __umulhi(q1, 0x80808081u) >> 7, e1 = q1 - q2 * 255u;
+    const uint32_t q3 = __umulhi(q2, 0x80808081u) >> 7, e2 = q2 - q3 * 255u;
+    return ((e0 - 127u) & 0xFFu) | (((e1 - 127u) & 0xFFu) << 8) | (((e2 - 127u) & 0xFFu) << 16) | (((q3 - 127u) & 0xFFu) << 24);
+}
+// x' (already * input_factor), |x'| < 2^e -> packed digits of the plane-scaled 23-bit integer
+// (imma_gemv.cuh: v = q << (7-j), -q for j = 7)
+__device__ __noinline__ uint32_t quant_digits(float xp, int e, int col) {
+    int q = __float2int_rn(xp * ldexpf(1.0f, 22 - e));
+    q = max(-(1 << 22), min(1 << 22, q));
+    const int j = col & 7;
+    const int v = (j == 7) ? -q : (q << (7 - j));
+    return digits255(v);
+}
+// mean / 1/sqrt(var + eps) of a LayerNorm (bitnet.py:118) from fp64 (sum, sum of squares) over n = 1/inv_n values
+__device__ __forceinline__ void ln_finish(double s, double q, double inv_n, float eps, float* mean, float* rstd) {
+    const double mu = s * inv_n;
+    const double var = fmax(q * inv_n - mu * mu, 0.0);  // biased variance
+    *mean = (float)mu;
+    *rstd = __frcp_rn(__fsqrt_rn((float)var + eps));
+}
+__device__ __forceinline__ double pow2d(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
+
+// word address (inside one [K]-word digit vector) of B-fragment word (plane j, digit d) of the 32-column block at col0
+__device__ __forceinline__ int frag_word(int col0, int j, int d) {
+    const int u = col0 >> 8, W = (col0 & 255) >> 5;
+    return u * 256 + (j >> 1) * 64 + d * 16 + (W >> 1) * 4 + (j & 1) * 2 + (W & 1);
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __noinline__ void put_hilo(uint32_t* p, uint32_t* pc, double v) {  // double as two publishable floats
+    const float hi = (float)v, lo = (float)(v - (double)hi);
+    stv1(p, fbits(hi));
+    stv1(p + 1, fbits(lo));
+    stv1(pc, kSentF);
+    stv1(pc + 1, kSentF);
+}
+
+// ---- the ring of weight tiles --------------------------------------------------------------------------------
+struct Ring {
+    uint32_t head, cap, seq;
+    __device__ __forceinline__ uint32_t alloc(uint32_t bytes, uint32_t& my_seq) {
+        if (head + bytes > cap) head = 0;
+        const uint32_t off = head;
+        head += bytes;
+        my_seq = seq++;
+        return off;
+    }
+};
+__device__ __forceinline__ void block_range(int nblocks, int cta, int ncta, int& b0, int& b1) {
+    b0 = (int)(((long long)nblocks * cta) / ncta);
+    b1 = (int)(((long long)nblocks * (cta + 1)) / ncta);
+}
+__device__ __host__ __forceinline__ int row_pitch(int kb) {  // bytes per weight row in the ring: = 32 (mod 128) -> conflict-free LDS.64
+    const int r = kb & 127;
+    return kb + ((32 - r + 128) & 127);
+}
+
+struct TileInfo {
+    uint32_t soff;     // byte offset of the tile inside the ring
+    int pslot;         // which digit set / scale the tile's rows use
+    const void* g;     // weight_scale of the tile's first row
+    int red_off;       // where the tile's K-group partial sums live in `red` (ints): [kgn][16][8]
+    int kgn;           // K groups of the pass the tile belongs to
+};
+__device__ __forceinline__ int tg_of(int n) { return n >= 4 ? 4 : (n >= 2 ? 2 : 1); }
+// tiles of a stage are processed in passes that fit the ring: the whole stage if possible, else 4 (or 2) at a time
+__device__ __forceinline__ int pass_size(int T, int tile_bytes, int ring_bytes) {
+    const int fit = ring_bytes / tile_bytes - 1;
+    return T <= fit ? max(T, 1) : (fit >= 4 ? 4 : 2);
+}
+
+// ---- shared-memory plan ---------------------------------------------------------------------------------------
+struct Smem {
+    unsigned char* ring;
+    uint32_t* dbuf;
+    int* red;
+    float* u;                     // [kMaxTok][192]
+    uint32_t* stat;               // [M * ncta * kStatW] (>= 3 * ncta * 4)
+    uint32_t* stage;              // [kMaxTok][96][3]
+    double* redd;                 // [32]
+    unsigned long long* q128;     // [2][kMaxTok]
+    double* invs;                 // [2][kMaxTok]
+    TileInfo* tile;               // [kMaxTiles]
+    float* fscr;                  // [64]
+};
+
+struct Ctx {
+    int tid, lane, warp, cta, ncta, M, H, I, pdt, ring_bytes, max_batch;
+    int nownC, colC0, om, oc;  // ownership of residual-stream columns: thread (om, oc) owns column colC0 + oc of token om
+    bool ownerC;
+    Smem S;
+    uint64_t* full;
+    uint64_t* empty;
+    int* abort_flag;
+    uint32_t* X;   // this step's exchange arena
+    uint32_t* Xc;  // the other parity set: re-armed (sentinels) word for word as we publish
+    Ring R;
+};
+
+// ---- Lamport copies global -> shared ------------------------------------------------------------------------
+// digit vector of K words: also commits this vector's Q128 = 128 * sum_k q_k to *q128 (integer, order independent)
+__device__ __noinline__ void poll_copy_d(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int nchunks, int tid, int lane,
+                                         unsigned long long* q128, int* abort_flag) {
+    constexpr int U = 6;
+    int se = 0, so = 0;
+    for (int base = 0; base < nchunks; base += kCT * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = base + k * kCT + tid;
+            v[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < nchunks) v[k] = ldv4(src + 4 * (size_t)i);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = base + k * kCT + tid;
+            if (i < nchunks) {
+                int spins = 0;
+                while (bad_d(v[k])) {
+                    if (spin_giveup(spins, abort_flag)) break;
+                    v[k] = ldv4(src + 4 * (size_t)i);
+                }
+                *reinterpret_cast<uint4*>(dst + 4 * (size_t)i) = v[k];
+                se = __dp4a((int)v[k].x, 0x01010101, se);
+                se = __dp4a((int)v[k].y, 0x01010101, se);
+                so = __dp4a((int)v[k].z, 0x01010101, so);
+                so = __dp4a((int)v[k].w, 0x01010101, so);
+            }
+        }
+    }
+    // thread tid always sees plane pair (tid>>4)&3 and digit (tid>>2)&3 (chunk index = tid mod 64 pattern)
+    const int d = (tid >> 2) & 3, jp = (tid >> 4) & 3;
+    const long long p255 = d == 0 ? 1ll : (d == 1 ? 255ll : (d == 2 ? 65025ll : 16581375ll));
+    const long long ce = 1ll << (2 * jp), co = (jp == 3) ? -128ll : (1ll << (2 * jp + 1));
+    long long c = p255 * ((long long)se * ce + (long long)so * co);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) atomicAdd(q128, (unsigned long long)c);
+}
+// float records: nchunks uint4 (nchunks may exceed kCT)
+__device__ __noinline__ void poll_copy_f(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int nchunks, int tid,
+                                         int* abort_flag) {
+    for (int i = tid; i < nchunks; i += kCT) {
+        uint4 v = ldv4(src + 4 * (size_t)i);
+        int spins = 0;
+        while (bad_f(v)) {
+            if (spin_giveup(spins, abort_flag)) break;
+            v = ldv4(src + 4 * (size_t)i);
+        }
+        *reinterpret_cast<uint4*>(dst + 4 * (size_t)i) = v;
+    }
+}
+
+// ---- IMMA phase: this warp's share (tile group x K group) of one pass of tiles [p0, p0 + n), partial sums to `red` --
+__device__ __forceinline__ void imma_phase(const unsigned char* ring, const TileInfo* s_tile, int p0, int n, int K, int pitch,
+                                           const uint32_t* dbuf, int set_words, int M, int* red, int warp, int lane) {
+    if (n <= 0) return;
+    const int TG = tg_of(n), KG = kCW / TG;
+    const int tg = warp / KG, kg = warp - tg * KG;
+    const int tpg = (n + TG - 1) / TG;
+    const int t0 = p0 + tg * tpg, nt = min(tpg, p0 + n - t0);
+    if (nt <= 0) return;
+    const int g = lane >> 2, t4 = lane & 3, units = K >> 8;
+    const int bm = g >> 2, bd = g & 3;
+    int acc[3][2][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0;
+    uint32_t soff[3];
+    int psl[3];
+#pragma unroll
+    for (int ti = 0; ti < 3; ++ti) {
+        const int tt = min(t0 + ti, p0 + n - 1);
+        soff[ti] = s_tile[tt].soff + (uint32_t)(g * pitch + 8 * t4);
+        psl[ti] = s_tile[tt].pslot;
+    }
+    for (int u = kg; u < units; u += KG) {
+        uint4 bv[4];
+        int loaded = -1;
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti) {
+            if (ti < nt) {
+                if (psl[ti] != loaded) {
+                    loaded = psl[ti];
+                    const uint32_t* bp = dbuf + (size_t)loaded * set_words + (size_t)bm * K + u * 256 + bd * 16 + t4 * 4;
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp)
+                        bv[jp] = bm < M ? *reinterpret_cast<const uint4*>(bp + jp * 64) : make_uint4(0u, 0u, 0u, 0u);
+                }
+                const unsigned char* wp = ring + soff[ti] + u * 32;
+                const uint2 w0 = *reinterpret_cast<const uint2*>(wp);
+                const uint2 w1 = *reinterpret_cast<const uint2*>(wp + 8 * pitch);
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp)
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const uint32_t mask = 0x01010101u << (2 * jp + jj);
+                        const uint32_t a0 = plane(w0.x, mask), a1 = plane(w1.x, mask);
+                        const uint32_t a2 = plane(w0.y, mask), a3 = plane(w1.y, mask);
+                        imma16832(acc[ti][jj], a0, a1, a2, a3, jj ? bv[jp].z : bv[jp].x, jj ? bv[jp].w : bv[jp].y);
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int ti = 0; ti < 3; ++ti) {
+        if (ti < nt) {
+            int* base = red + s_tile[t0 + ti].red_off + kg * 128 + 2 * t4;
+            *reinterpret_cast<int2*>(base + g * 8) = make_int2(acc[ti][0][0] + acc[ti][1][0], acc[ti][0][1] + acc[ti][1][1]);
+            *reinterpret_cast<int2*>(base + (g + 8) * 8) = make_int2(acc[ti][0][2] + acc[ti][1][2], acc[ti][0][3] + acc[ti][1][3]);
+        }
+    }
+}
+// row result of the stage: t = sum_k s(n,k) x'_k for (row r of tile ti, token em), from the K-group partial sums
+__device__ __noinline__ float row_value(const int* red, const TileInfo* ti, int r, int em, long long q128, double invs) {
+    int4 a = make_int4(0, 0, 0, 0);
+    const int* p = red + ti->red_off + r * 8 + 4 * em;
+    for (int kg = 0; kg < ti->kgn; ++kg) {
+        const int4 v = *reinterpret_cast<const int4*>(p + kg * 128);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const long long V = (((long long)a.w * 255 + a.z) * 255 + a.y) * 255 + a.x;  // = 128 * sum_{bit=1} q
+    return (float)((double)(q128 - 2 * V) * invs);                               // invs = 2^(e-22) / 128
+}
+
+// describe tile i of a T-tile stage (executed by thread i while every thread walks the ring allocator)
+__device__ __noinline__ void put_tile(Ctx& c, int i, int T, int pitch, uint32_t off, int pslot, const void* gbase, int row0) {
+    TileInfo& t = c.S.tile[i];
+    t.soff = off;
+    t.pslot = pslot;
+    t.g = static_cast<const char*>(gbase) + (size_t)row0 * dsize(c.pdt);
+    const int ps = pass_size(T, 16 * pitch, c.ring_bytes);
+    const int p = i / ps, n = min(ps, T - p * ps);
+    t.kgn = kCW / tg_of(n);
+    t.red_off = (p * ps * (kCW / tg_of(ps)) + (i - p * ps) * t.kgn) * 128;
+}
+
+// generic BitLinear stage core: copy the input digit vectors (Lamport poll), run the IMMA passes, release the tiles.
+// `seq0`: ring sequence number of the stage's first tile (its T tiles are consecutive chunks).
+__device__ __noinline__ void stage_core(Ctx& c, int K, int pitch, int T, uint32_t seq0, int nsets, const uint32_t* x0, const uint32_t* x1) {
+    const int set_words = c.M * K;
+    if (T > 0) {
+        for (int ps = 0; ps < nsets; ++ps)
+            for (int m = 0; m < c.M; ++m)
+                poll_copy_d((ps ? x1 : x0) + (size_t)m * K, c.S.dbuf + (size_t)ps * set_words + (size_t)m * K, K / 4, c.tid, c.lane,
+                            &c.S.q128[ps * kMaxTok + m], c.abort_flag);
+    }
+    const int psz = pass_size(T, 16 * pitch, c.ring_bytes);
+    for (int p0 = 0; p0 < max(T, 1); p0 += psz) {
+        const int n = min(psz, T - p0);
+        if (c.warp < n && c.lane == 0) {
+            const uint32_t sq = seq0 + (uint32_t)(p0 + c.warp);
+            mbar_wait(&c.full[sq % kNB], (sq / kNB) & 1);
+        }
+        cta_sync();
+        imma_phase(c.S.ring, c.S.tile, p0, n, K, pitch, c.S.dbuf, set_words, c.M, c.S.red, c.warp, c.lane);
+        cta_sync();
+        if (c.tid < n) mbar_arrive(&c.empty[(seq0 + (uint32_t)(p0 + c.tid)) % kNB]);
+    }
+}
+
+// publish the digits of `nprob` BitLinear inputs for the owned 32-column blocks: S.stage[(m*nprob+p)*nown + col] holds
+// the four packed digits of column col; every (plane, digit) word of the B-fragment layout is assembled from 4 columns
+__device__ __noinline__ void publish32(Ctx& c, size_t xoff, size_t prob_stride, size_t tok_stride, int nprob, int nown, int col0) {
+    const int nblk = nown >> 5;
+    if (nblk <= 0) return;
+    const int items = kMaxTok * nprob * nblk * 32;
+    for (int it = c.tid; it < items; it += kCT) {
+        const int jd = it & 31, j = jd >> 2, d = jd & 3;
+        int r = it >> 5;
+        const int blk = r % nblk; r /= nblk;
+        const int p = r % nprob, m = r / nprob;
+        const size_t a = xoff + (size_t)p * prob_stride + (size_t)m * tok_stride + frag_word(col0 + blk * 32, j, d);
+        if (m < c.M) {
+            const uint32_t* sp = c.S.stage + (size_t)(m * nprob + p) * nown + blk * 32 + j;
+            const uint32_t sel = (uint32_t)d | ((uint32_t)(4 + d) << 4);
+            const uint32_t lo = __byte_perm(sp[0], sp[8], sel), hi = __byte_perm(sp[16], sp[24], sel);
+            stv1(c.X + a, __byte_perm(lo, hi, 0x5410));
+        }
+        // re-arm the other parity set for every token slot (a later step may run a larger batch)
+        if (m < c.max_batch) stv1(c.Xc + a, kSentD);
+    }
+}
+// same for 16-column blocks (stage D1): each fragment word gets a 16-bit half from this CTA
+__device__ __noinline__ void publish16(Ctx& c, size_t xoff, size_t tok_stride, int npb, int col0) {
+    const int nown = 16 * npb, items = kMaxTok * npb * 32;
+    for (int it = c.tid; it < items; it += kCT) {
+        const int jd = it & 31, j = jd >> 2, d = jd & 3;
+        const int r = it >> 5, blk = r % npb, m = r / npb;
+        const int c0 = col0 + blk * 16;
+        const size_t a = xoff + (size_t)m * tok_stride + frag_word(c0 & ~31, j, d);
+        const int bo = (c0 & 16) ? 2 : 0;
+        if (m < c.M) {
+            const uint32_t* sp = c.S.stage + m * nown + blk * 16 + j;
+            stv16(reinterpret_cast<char*>(c.X + a) + bo, __byte_perm(sp[0], sp[8], (uint32_t)d | ((uint32_t)(4 + d) << 4)) & 0xFFFFu);
+        }
+        if (m < c.max_batch) stv16(reinterpret_cast<char*>(c.Xc + a) + bo, 0x8080u);
+    }
+}
+
+// exchange of per-CTA statistics records [M][ncta][kStatW]: poll every CTA's record, then reduce in a fixed order:
+// quantity q < nq is a sum of (hi, lo) pairs, the nmax quantities after are maxima. Result: S.redd[m * (nq + nmax) + q].
+__device__ __noinline__ void stats_exchange(Ctx& c, size_t soff, int nq, int nmax) {
+    for (int m = 0; m < c.M; ++m)
+        poll_copy_f(c.X + soff + (size_t)m * c.ncta * kStatW, c.S.stat + (size_t)m * c.ncta * kStatW, c.ncta * kStatW / 4, c.tid, c.abort_flag);
+    cta_sync();
+    const int per = nq + nmax;
+    if (c.warp < per * c.M) {
+        const int m = c.warp / per, qn = c.warp - m * per;
+        const float* st = reinterpret_cast<const float*>(c.S.stat) + (size_t)m * c.ncta * kStatW;
+        if (qn < nq) {
+            double s = 0.0;
+            for (int k = c.lane; k < c.ncta; k += 32) s += (double)st[k * kStatW + 2 * qn] + (double)st[k * kStatW + 2 * qn + 1];
+            s = warp_sum_d(s);
+            if (c.lane == 0) c.S.redd[c.warp] = s;
+        } else {
+            float mx = 0.f;
+            for (int k = c.lane; k < c.ncta; k += 32) mx = fmaxf(mx, st[k * kStatW + 2 * nq + (qn - nq)]);
+            mx = warp_max_f(mx);
+            if (c.lane == 0) c.S.redd[c.warp] = (double)mx;
+        }
+    }
+    cta_sync();
+}
+
+// x_hat = resid * rr[token] * ln_w -> x' for q, k, v of layer l -> digits -> exchange (inputs of stage A)   (:67-81)
+__device__ __noinline__ void publish_qkv_inputs(Ctx& c, const Params& P, int l, const void* lnw, float resid, const float* rr) {
+    const LayerDev& Ly = P.layers[l];
+    if (c.ownerC) {
+        const int col = c.colC0 + c.oc;
+        const float xh = resid * rr[c.om] * ldp(lnw, col, c.pdt);
+        c.S.stage[(size_t)(c.om * 3 + 0) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.q.h, col, c.pdt), Ly.e_qkv[0], col);
+        c.S.stage[(size_t)(c.om * 3 + 1) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.k.h, col, c.pdt), Ly.e_qkv[1], col);
+        c.S.stage[(size_t)(c.om * 3 + 2) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.v.h, col, c.pdt), Ly.e_qkv[2], col);
+    }
+    cta_sync();
+    publish32(c, (size_t)l * P.per_layer + P.o_xA, (size_t)kMaxTok * c.H, (size_t)c.H, 3, c.nownC, c.colC0);
+}
+
+// stages C / D2 share their shape: rows of o_proj / down_proj owned as 32-row blocks, then
+// x <- x + LayerNorm(g*t) (:912 / :918) and the RMSNorm factor of the next BitLinear group (:67-81), all from ONE
+// exchange of five per-CTA sums (sum u, sum u^2, sum r, sum r^2, sum r*u).
+__device__ __noinline__ void residual_stage(Ctx& c, const Params& P, const BLDev* bl, int K, int pitch, const uint32_t* xin0, size_t o_stat,
+                                            float* resid_io, float* rr_out /*[M]*/) {
+    const int T = c.nownC >> 4;
+    const uint32_t seq0 = c.R.seq;
+    for (int i = 0; i < T; ++i) {
+        uint32_t seq;
+        const uint32_t off = c.R.alloc(16u * pitch, seq);
+        if (c.tid == i) put_tile(c, i, T, pitch, off, 0, bl->g, c.colC0 + 16 * i);
+    }
+    stage_core(c, K, pitch, T, seq0, 1, xin0, xin0);
+    float u = 0.f, resid = *resid_io;
+    if (c.ownerC) {
+        const TileInfo* ti = &c.S.tile[c.oc >> 4];
+        u = row_value(c.S.red, ti, c.oc & 15, c.om, (long long)c.S.q128[c.om], c.S.invs[c.om]) * ldp(ti->g, c.oc & 15, c.pdt);
+        c.S.u[c.om * 192 + c.oc] = u;
+        c.S.u[c.om * 192 + 96 + c.oc] = resid;
+    }
+    cta_sync();
+    if (c.tid < 2 * kMaxTok) c.S.q128[c.tid] = 0ull;
+    if (c.warp < kMaxTok) {  // this CTA's five sums per token
+        const int m = c.warp;
+        double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (m < c.M)
+            for (int k = c.lane; k < c.nownC; k += 32) {
+                const double uu = (double)c.S.u[m * 192 + k], r = (double)c.S.u[m * 192 + 96 + k];
+                s[0] += uu; s[1] += uu * uu; s[2] += r; s[3] += r * r; s[4] += r * uu;
+            }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s[i] = warp_sum_d(s[i]);
+        if (c.lane == 0 && m < c.max_batch) {
+            const size_t a = o_stat + ((size_t)m * c.ncta + c.cta) * kStatW;
+            if (m < c.M) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) put_hilo(c.X + a + 2 * i, c.Xc + a + 2 * i, s[i]);
+                stv1(c.X + a + 10, 0u); stv1(c.X + a + 11, 0u);
+                stv1(c.Xc + a + 10, kSentF); stv1(c.Xc + a + 11, kSentF);
+            } else {
+                for (int i = 0; i < kStatW; ++i) stv1(c.Xc + a + i, kSentF);
+            }
+        }
+    }
+    stats_exchange(c, o_stat, 5, 0);
+    if (c.tid < c.M) {  // one thread per token: LayerNorm statistics and the RMSNorm factor of the updated stream
+        const double* rd = c.S.redd + c.tid * 5;
+        const double N = (double)c.H;
+        float mean, rstd;
+        ln_finish(rd[0], rd[1], P.inv_H, P.ln_eps, &mean, &rstd);
+        const double mu = (double)mean, rs = (double)rstd;
+        // sum over the full width of (r + (u - mu) rs)^2, with the SAME rounded mean / rstd the owners apply
+        const double ssq = rd[3] + 2.0 * rs * (rd[4] - mu * rd[2]) + rs * rs * (rd[1] - 2.0 * mu * rd[0] + N * mu * mu);
+        c.S.fscr[c.tid] = rsqrtf((float)(fmax(ssq, 0.0) * P.inv_H) + P.rms_eps);  // LlamaRMSNorm
+        c.S.fscr[kMaxTok + c.tid] = mean;
+        c.S.fscr[2 * kMaxTok + c.tid] = rstd;
+    }
+    cta_sync();
+    if (c.ownerC) *resid_io = resid + (u - c.S.fscr[kMaxTok + c.om]) * c.S.fscr[2 * kMaxTok + c.om];
+    for (int m = 0; m < c.M; ++m) rr_out[m] = c.S.fscr[m];
+}
+
+// stage A: q, k, v = BitLinear(RMSNorm(x)) (:522-524) — publishes raw g*t and per-CTA LayerNorm partials
+__device__ __noinline__ void stage_qkv(Ctx& c, const Params& P, int l, int a_b0, int a_b1, const int* s_pos) {
+    const LayerDev& Ly = P.layers[l];
+    const int H = c.H, tH = H >> 4, pitchH = row_pitch(H >> 3);
+    const int gt0 = 2 * a_b0, gt1 = 2 * a_b1, T = gt1 - gt0;
+    const int p_lo = gt0 / tH, nsets = (gt1 - 1) / tH - p_lo + 1;
+    uint32_t* XL = c.X + (size_t)l * P.per_layer;
+    uint32_t* XLc = c.Xc + (size_t)l * P.per_layer;
+    const uint32_t seq0 = c.R.seq;
+    for (int i = 0; i < T; ++i) {
+        uint32_t seq;
+        const uint32_t off = c.R.alloc(16u * pitchH, seq);
+        if (c.tid == i) {
+            const int gt = gt0 + i, prob = gt / tH, row0 = (gt - prob * tH) * 16;
+            const BLDev& b = prob == 0 ? Ly.q : (prob == 1 ? Ly.k : Ly.v);
+            put_tile(c, i, T, pitchH, off, prob - p_lo, b.g, row0);
+        }
+    }
+    if (c.tid < 2 * kMaxTok) c.S.invs[c.tid] = pow2d(Ly.e_qkv[min(p_lo + c.tid / kMaxTok, 2)] - 29);
+    // attention CTAs: pull this layer's cached K/V rows of their (sequence, head) towards L2
+    if (c.cta < P.heads * c.M) {
+        const int am = c.cta / P.heads, ah = c.cta - am * P.heads;
+        const size_t base = ((((size_t)l * P.max_batch + am) * P.heads + ah) * P.max_seq) * kHeadDim;
+        const int lines = s_pos[am] * 2;  // 256 B per row = 2 x 128 B lines
+        for (int i = c.tid; i < lines; i += kCT) {
+            prefetch_l2(reinterpret_cast<const char*>(P.kcache + base) + (size_t)i * 128);
+            prefetch_l2(reinterpret_cast<const char*>(P.vcache + base) + (size_t)i * 128);
+        }
+    }
+    stage_core(c, H, pitchH, T, seq0, nsets, XL + P.o_xA + (size_t)p_lo * kMaxTok * H, XL + P.o_xA + (size_t)min(p_lo + 1, 2) * kMaxTok * H);
+    const int Rr = 16 * T;
+    if (c.tid < Rr * kMaxTok) {
+        const int em = c.tid / Rr, er = c.tid - em * Rr;
+        const int gt = gt0 + (er >> 4), prob = gt / tH, row = (gt - prob * tH) * 16 + (er & 15);
+        const size_t a = P.o_qkv + ((size_t)em * 3 + prob) * H + row;
+        if (em < c.M) {
+            const TileInfo* ti = &c.S.tile[er >> 4];
+            const float u = row_value(c.S.red, ti, er & 15, em, (long long)c.S.q128[ti->pslot * kMaxTok + em], c.S.invs[ti->pslot * kMaxTok + em]) *
+                            ldp(ti->g, er & 15, c.pdt);
+            c.S.u[em * 192 + er] = u;
+            stv1(XL + a, fbits(u));
+        }
+        if (em < c.max_batch) stv1(XLc + a, kSentF);
+    }
+    cta_sync();
+    if (c.tid < 2 * kMaxTok) c.S.q128[c.tid] = 0ull;
+    if (c.warp < 3 * kMaxTok) {  // per-(token, projection) partial (sum, sum of squares) of this CTA's rows
+        const int m = c.warp / 3, p = c.warp - 3 * m;
+        double s = 0.0, q = 0.0;
+        if (m < c.M)
+            for (int r = c.lane; r < Rr; r += 32)
+                if ((gt0 + (r >> 4)) / tH == p) {
+                    const double v = (double)c.S.u[m * 192 + r];
+                    s += v;
+                    q += v * v;
+                }
+        s = warp_sum_d(s);
+        q = warp_sum_d(q);
+        if (c.lane == 0 && m < c.max_batch) {
+            const size_t a = P.o_qst + (((size_t)m * 3 + p) * c.ncta + c.cta) * 4;
+            if (m < c.M) {
+                put_hilo(XL + a, XLc + a, s);
+                put_hilo(XL + a + 2, XLc + a + 2, q);
+            } else {
+                for (int i = 0; i < 4; ++i) stv1(XLc + a + i, kSentF);
+            }
+        }
+    }
+}
+
+// stage B: attention for one new token per sequence (:536-563): LayerNorm of q/k/v (bitnet.py:118) from the partials,
+// RoPE (:176-181), cache append, fp32 online softmax over the cache, digits of o_proj's input
+__device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, const int* s_pos) {
+    const LayerDev& Ly = P.layers[l];
+    const int H = c.H, tid = c.tid, lane = c.lane, warp = c.warp, ncta = c.ncta;
+    uint32_t* XL = c.X + (size_t)l * P.per_layer;
+    uint32_t* XLc = c.Xc + (size_t)l * P.per_layer;
+    if (c.cta >= P.heads * c.M) {
+        if (c.cta < P.heads * P.max_batch && tid < 128) {  // a larger batch would publish here: keep the other set armed
+            const int am = c.cta / P.heads, ah = c.cta - am * P.heads;
+            stv1(XLc + P.o_xC + (size_t)am * H + frag_word(ah * kHeadDim + (tid >> 5) * 32, (tid & 31) >> 2, tid & 3), kSentD);
+        }
+        return;
+    }
+    const int am = c.cta / P.heads, ah = c.cta - am * P.heads;
+    const int pos = s_pos[am], Tctx = pos + 1;
+    float* raw = reinterpret_cast<float*>(c.S.red);  // [3][128] raw q, k, v of this head
+    float* sq = raw + 384;                            // [128] rotated, scaled q
+    float* sk = sq + 128;                             // [128] new k row (fp16-rounded)
+    float* sv = sk + 128;                             // [128] new v row (fp16-rounded)
+    float* part = sv + 128;                           // [16][132]: m, l, o[128] per warp
+    poll_copy_f(XL + P.o_qst + (size_t)am * 3 * ncta * 4, c.S.stat, 3 * ncta, tid, c.abort_flag);
+    if (tid < 96) {
+        const int p = tid >> 5, i = tid & 31;
+        const uint32_t* src = XL + P.o_qkv + ((size_t)am * 3 + p) * H + ah * kHeadDim + 4 * i;
+        uint4 v = ldv4(src);
+        int spins = 0;
+        while (bad_f(v)) {
+            if (spin_giveup(spins, c.abort_flag)) break;
+            v = ldv4(src);
+        }
+        *reinterpret_cast<uint4*>(raw + p * 128 + 4 * i) = v;
+    }
+    cta_sync();
+    if (warp < 6) {  // (projection, sum | sumsq): fixed-order reduction over the CTAs
+        const int p = warp >> 1, which = warp & 1;
+        const float* st = reinterpret_cast<const float*>(c.S.stat) + (size_t)p * ncta * 4 + 2 * which;
+        double s = 0.0;
+        for (int k = lane; k < ncta; k += 32) s += (double)st[k * 4] + (double)st[k * 4 + 1];
+        s = warp_sum_d(s);
+        if (lane == 0) c.S.redd[warp] = s;
+    }
+    cta_sync();
+    if (tid < 3) ln_finish(c.S.redd[2 * tid], c.S.redd[2 * tid + 1], P.inv_H, P.ln_eps, &c.S.fscr[2 * tid], &c.S.fscr[2 * tid + 1]);
+    cta_sync();
+    __half* kc = P.kcache + ((((size_t)l * P.max_batch + am) * P.heads + ah) * P.max_seq) * kHeadDim;
+    __half* vc = P.vcache + ((((size_t)l * P.max_batch + am) * P.heads + ah) * P.max_seq) * kHeadDim;
+    if (tid < kHeadDim) {
+        const float mean[3] = {c.S.fscr[0], c.S.fscr[2], c.S.fscr[4]}, rstd[3] = {c.S.fscr[1], c.S.fscr[3], c.S.fscr[5]};
+        const int d = tid, half = kHeadDim / 2, dp = d < half ? d + half : d - half, fi = d < half ? d : d - half;
+        const float cs = P.rope_cos[(size_t)pos * half + fi], sn = P.rope_sin[(size_t)pos * half + fi];
+        const float q0 = (raw[d] - mean[0]) * rstd[0], q1 = (raw[dp] - mean[0]) * rstd[0];
+        const float k0 = (raw[128 + d] - mean[1]) * rstd[1], k1 = (raw[128 + dp] - mean[1]) * rstd[1];
+        const float qr = d < half ? q0 * cs - q1 * sn : q0 * cs + q1 * sn;  // rotate_half: (-x2, x1), :168-181
+        const float kr = d < half ? k0 * cs - k1 * sn : k0 * cs + k1 * sn;
+        const float vv = (raw[256 + d] - mean[2]) * rstd[2];
+        const __half kh = __float2half_rn(kr), vh = __float2half_rn(vv);
+        kc[(size_t)pos * kHeadDim + d] = kh;
+        vc[(size_t)pos * kHeadDim + d] = vh;
+        sq[d] = qr * 0.08838834764831845f;  // 1 / sqrt(128), :546
+        sk[d] = __half2float(kh);
+        sv[d] = __half2float(vh);
+    }
+    cta_sync();
+    {   // each warp: online softmax over positions warp, warp+16, ...; lane holds dims 4*lane .. 4*lane+3
+        const float4 qv = *reinterpret_cast<const float4*>(sq + 4 * lane);
+        float mx = -INFINITY, lsum = 0.f;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j0 = warp; j0 < Tctx; j0 += 4 * kCW) {
+            uint2 kr[4], vr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * kCW;
+                kr[u] = make_uint2(0u, 0u);
+                vr[u] = make_uint2(0u, 0u);
+                if (j < pos) {
+                    kr[u] = *reinterpret_cast<const uint2*>(kc + (size_t)j * kHeadDim + 4 * lane);
+                    vr[u] = *reinterpret_cast<const uint2*>(vc + (size_t)j * kHeadDim + 4 * lane);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * kCW;
+                if (j < Tctx) {
+                    float4 kf, vf;
+                    if (j < pos) {
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&kr[u].x));
+                        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&kr[u].y));
+                        const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&vr[u].x));
+                        const float2 d2 = __half22float2(*reinterpret_cast<const __half2*>(&vr[u].y));
+                        kf = make_float4(a.x, a.y, b.x, b.y);
+                        vf = make_float4(c2.x, c2.y, d2.x, d2.y);
+                    } else {
+                        kf = *reinterpret_cast<const float4*>(sk + 4 * lane);
+                        vf = *reinterpret_cast<const float4*>(sv + 4 * lane);
+                    }
+                    float dot = qv.x * kf.x + qv.y * kf.y + qv.z * kf.z + qv.w * kf.w;
+                    dot = warp_sum(dot);
+                    const float mn = fmaxf(mx, dot);
+                    const float sc = expf(mx - mn), pj = expf(dot - mn);
+                    lsum = lsum * sc + pj;
+                    o.x = o.x * sc + pj * vf.x; o.y = o.y * sc + pj * vf.y;
+                    o.z = o.z * sc + pj * vf.z; o.w = o.w * sc + pj * vf.w;
+                    mx = mn;
+                }
+            }
+        }
+        float* pw = part + warp * 132;
+        if (lane == 0) { pw[0] = mx; pw[1] = lsum; }
+        *reinterpret_cast<float4*>(pw + 4 + 4 * lane) = o;
+    }
+    cta_sync();
+    if (tid < kHeadDim) {
+        float mx = -INFINITY;
+        for (int w = 0; w < kCW; ++w) mx = fmaxf(mx, part[w * 132]);
+        float den = 0.f, num = 0.f;
+        for (int w = 0; w < kCW; ++w) {
+            const float m_w = part[w * 132];
+            const float f = m_w == -INFINITY ? 0.f : expf(m_w - mx);
+            den += part[w * 132 + 1] * f;
+            num += part[w * 132 + 4 + tid] * f;
+        }
+        const int col = ah * kHeadDim + tid;
+        c.S.stage[tid] = quant_digits((num / den) * ldp(Ly.o.h, col, c.pdt), Ly.e_o, col);
+    }
+    cta_sync();
+    if (tid < 128) {
+        const int blk = tid >> 5, jd = tid & 31, j = jd >> 2, d = jd & 3;
+        const uint32_t* sp = c.S.stage + blk * 32 + j;
+        const uint32_t sel = (uint32_t)d | ((uint32_t)(4 + d) << 4);
+        const uint32_t word = __byte_perm(__byte_perm(sp[0], sp[8], sel), __byte_perm(sp[16], sp[24], sel), 0x5410);
+        const size_t a = P.o_xC + (size_t)am * H + frag_word(ah * kHeadDim + blk * 32, j, d);
+        stv1(XL + a, word);
+        stv1(XLc + a, kSentD);
+    }
+}
+
+// stage D1: gate, up (:257) — 16 gate rows + 16 up rows of the same columns live in the same CTA, so
+// silu(LN(gate)) * LN(up) * input_factor(down) is finished by the owner after ONE exchange of sums and bounds
+__device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d_b0, int d_b1) {
+    const LayerDev& Ly = P.layers[l];
+    const int H = c.H, I = c.I, pitchH = row_pitch(H >> 3), tid = c.tid, lane = c.lane, warp = c.warp;
+    (void)I;
+    uint32_t* XL = c.X + (size_t)l * P.per_layer;
+    uint32_t* XLc = c.Xc + (size_t)l * P.per_layer;
+    const int npb = d_b1 - d_b0, T = 2 * npb, nown = 16 * npb, col0 = 16 * d_b0;
+    const uint32_t seq0 = c.R.seq;
+    for (int i = 0; i < T; ++i) {
+        uint32_t seq;
+        const uint32_t off = c.R.alloc(16u * pitchH, seq);
+        if (tid == i) {
+            const bool up = i >= npb;
+            put_tile(c, i, T, pitchH, off, up ? 1 : 0, up ? Ly.up.g : Ly.gate.g, 16 * (d_b0 + (up ? i - npb : i)));
+        }
+    }
+    if (tid < 2 * kMaxTok) c.S.invs[tid] = pow2d(Ly.e_gu[tid / kMaxTok] - 29);
+    stage_core(c, H, pitchH, T, seq0, 2, XL + P.o_xD1, XL + P.o_xD1 + (size_t)kMaxTok * H);
+    const int Rr = 16 * T;
+    if (Rr > 0) {
+        const int em = tid / Rr, er = tid - em * Rr;
+        if (em < c.M) {
+            const TileInfo* ti = &c.S.tile[er >> 4];
+            c.S.u[em * 192 + er] = row_value(c.S.red, ti, er & 15, em, (long long)c.S.q128[ti->pslot * kMaxTok + em], c.S.invs[ti->pslot * kMaxTok + em]) *
+                                   ldp(ti->g, er & 15, c.pdt);
+        }
+    }
+    cta_sync();
+    if (tid < 2 * kMaxTok) c.S.q128[tid] = 0ull;
+    const bool ownerD = tid < nown * c.M;
+    const int dm = ownerD ? tid / nown : 0, dc = ownerD ? tid - dm * nown : 0;
+    float gv = 0.f, uv = 0.f, hd = 0.f;
+    if (ownerD) {
+        gv = c.S.u[dm * 192 + dc];
+        uv = c.S.u[dm * 192 + nown + dc];
+        hd = ldp(Ly.down.h, col0 + dc, c.pdt);
+    }
+    if (warp < kMaxTok) {
+        const int m = warp;
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        float mx[3] = {0.f, 0.f, 0.f};
+        if (m < c.M)
+            for (int k = lane; k < nown; k += 32) {
+                const float gf = c.S.u[m * 192 + k], uf = c.S.u[m * 192 + nown + k], hf = fabsf(ldp(Ly.down.h, col0 + k, c.pdt));
+                s[0] += (double)gf; s[1] += (double)gf * (double)gf; s[2] += (double)uf; s[3] += (double)uf * (double)uf;
+                mx[0] = fmaxf(mx[0], fabsf(gf * uf) * hf); mx[1] = fmaxf(mx[1], fabsf(gf) * hf); mx[2] = fmaxf(mx[2], fabsf(uf) * hf);
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] = warp_sum_d(s[i]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) mx[i] = warp_max_f(mx[i]);
+        if (lane == 0 && m < c.max_batch) {
+            const size_t a = P.o_dst + ((size_t)m * c.ncta + c.cta) * kStatW;
+            if (m < c.M) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) put_hilo(XL + a + 2 * i, XLc + a + 2 * i, s[i]);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { stv1(XL + a + 8 + i, fbits(mx[i])); stv1(XLc + a + 8 + i, kSentF); }
+                stv1(XL + a + 11, 0u); stv1(XLc + a + 11, kSentF);
+            } else {
+                for (int i = 0; i < kStatW; ++i) stv1(XLc + a + i, kSentF);
+            }
+        }
+    }
+    stats_exchange(c, (size_t)l * P.per_layer + P.o_dst, 4, 3);
+    if (tid < c.M) {  // per token: LayerNorm statistics of gate and up, power-of-two bound of down_proj's input
+        const double* rd = c.S.redd + tid * 7;
+        float mg, rg, mu, ru;
+        ln_finish(rd[0], rd[1], P.inv_I, P.ln_eps, &mg, &rg);
+        ln_finish(rd[2], rd[3], P.inv_I, P.ln_eps, &mu, &ru);
+        const float amg = fabsf(mg), amu = fabsf(mu);
+        // |silu(g^) u^ h| <= |g^||u^||h| <= rg ru (|g u h| + |mg||u h| + |mu||g h| + |mg mu||h|)
+        const float bound = rg * ru * ((float)rd[4] + amg * (float)rd[6] + amu * (float)rd[5] + amg * amu * Ly.hmax_down) * 1.0001f;
+        int e = 0;
+        if (bound > 0.f && bound < 3.0e38f) frexpf(bound, &e);
+        float* f = c.S.fscr + tid * 8;
+        f[0] = mg; f[1] = rg; f[2] = mu; f[3] = ru;
+        reinterpret_cast<int*>(f)[4] = e;
+        c.S.invs[tid] = pow2d(e - 29);  // scale of down_proj's input digits (pslot 0)
+    }
+    cta_sync();
+    if (ownerD) {
+        const float* f = c.S.fscr + dm * 8;
+        const float gh = (gv - f[0]) * f[1], uh = (uv - f[2]) * f[3];
+        const float act = __fdiv_rn(gh, 1.0f + expf(-gh)) * uh;  // act_fn(gate) * up, :257
+        c.S.stage[dm * nown + dc] = quant_digits(act * hd, reinterpret_cast<const int*>(f)[4], col0 + dc);
+    }
+    cta_sync();
+    publish16(c, (size_t)l * P.per_layer + P.o_xD2, (size_t)I, npb, col0);
+}
+
+// lm_head (:1610-1611) + greedy argmax (generation/utils.py:2540): one fp16 row per ring chunk, one warp per row
+__device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, int v_b1, float* __restrict__ logits, const int* s_pos,
+                                           unsigned long long step, unsigned long long* tr) {
+    const int H = c.H, M = c.M, tid = c.tid, lane = c.lane, warp = c.warp, ncta = c.ncta;
+    uint32_t* Xt = c.X + (size_t)P.L * P.per_layer;
+    uint32_t* Xtc = c.Xc + (size_t)P.L * P.per_layer;
+    uint32_t* xs = c.S.dbuf;  // [M][H/2] half2 words
+    for (int m = 0; m < M; ++m) poll_copy_f(Xt + P.o_xfin + (size_t)m * (H / 2), xs + (size_t)m * (H / 2), H / 8, tid, c.abort_flag);
+    cta_sync();
+    float best[kMaxTok];
+    int bidx[kMaxTok];
+#pragma unroll
+    for (int m = 0; m < kMaxTok; ++m) { best[m] = -INFINITY; bidx[m] = 0x7fffffff; }
+    const int nch = H / 8;  // uint4 chunks per row
+    for (int v = v_b0; v < v_b1; ++v) {
+        uint32_t seq;
+        const uint32_t off = c.R.alloc((uint32_t)(2 * H), seq);
+        if ((int)(seq % kCW) != warp) continue;
+        mbar_wait(&c.full[seq % kNB], (seq / kNB) & 1);
+        const uint4* wr = reinterpret_cast<const uint4*>(c.S.ring + off);
+        float acc[kMaxTok] = {0.f, 0.f};
+        for (int i = lane; i < nch; i += 32) {
+            const uint4 wv = wr[i];
+            const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+            for (int m = 0; m < kMaxTok; ++m) {
+                if (m < M) {
+                    const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)m * (H / 2))[i];
+                    const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 a = __half22float2(w2[q]), b = __half22float2(x2[q]);
+                        acc[m] += a.x * b.x + a.y * b.y;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c.empty[seq % kNB]);
+#pragma unroll
+        for (int m = 0; m < kMaxTok; ++m) {
+            if (m < M) {
+                const float r = warp_sum(acc[m]);
+                if (lane == 0) logits[(size_t)m * P.V + v] = r;
+                if (r > best[m] || (r == best[m] && v < bidx[m])) { best[m] = r; bidx[m] = v; }
+            }
+        }
+    }
+    float* sb = c.S.fscr;                                        // [kCW][kMaxTok] values
+    int* si = reinterpret_cast<int*>(c.S.fscr + kCW * kMaxTok);  // [kCW][kMaxTok] indices
+    if (lane == 0)
+        for (int m = 0; m < kMaxTok; ++m) { sb[warp * kMaxTok + m] = best[m]; si[warp * kMaxTok + m] = bidx[m]; }
+    cta_sync();
+    if (tid < kMaxTok && tid < c.max_batch) {
+        const int m = tid;
+        const size_t a = P.o_amax + ((size_t)m * ncta + c.cta) * 2;
+        if (m < M) {
+            float b = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int w = 0; w < kCW; ++w) {
+                const float x = sb[w * kMaxTok + m];
+                const int xi = si[w * kMaxTok + m];
+                if (x > b || (x == b && xi < bi)) { b = x; bi = xi; }
+            }
+            stv1(Xt + a, fbits(b));
+            stv1(Xt + a + 1, (uint32_t)bi);
+        }
+        stv1(Xtc + a, kSentF);
+        stv1(Xtc + a + 1, kSentF);
+    }
+    if (c.cta == 0) {
+        poll_copy_f(Xt + P.o_amax, c.S.stat, M * ncta * 2 / 4, tid, c.abort_flag);  // ncta even: whole uint4s
+        cta_sync();
+        if (tid < M) {
+            const int m = tid;
+            float b = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int k = 0; k < ncta; ++k) {
+                const float x = __uint_as_float(c.S.stat[(m * ncta + k) * 2]);
+                const int xi = (int)c.S.stat[(m * ncta + k) * 2 + 1];
+                if (x > b || (x == b && xi < bi)) { b = x; bi = xi; }
+            }
+            P.ids[m] = bi == 0x7fffffff ? 0 : bi;
+            P.pos[m] = s_pos[m] + 1;
+        }
+        cta_sync();
+        if (tid == 0) {
+            tr[1] = gtime();
+            __threadfence();
+            *P.step_counter = step + 1ull;
+        }
+    }
+}
+
+// TMA producer warp: walks the static schedule of this CTA's weight tiles, independent of the dependency chain
+__device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_raw, int ring_bytes, uint64_t* s_full, uint64_t* s_empty,
+                                           uint32_t* s_qoff, uint32_t* s_qsz, int lane, int a_b0, int a_b1, int c_b0, int c_b1, int d_b0,
+                                           int d_b1, int v_b0, int v_b1) {
+    const int H = P.H, I = P.I, KbH = H >> 3, KbI = I >> 3, pitchH = row_pitch(KbH), pitchI = row_pitch(KbI), tH = H >> 4;
+    Ring R;
+    R.head = 0; R.cap = (uint32_t)ring_bytes; R.seq = 0;
+    uint32_t q_tail = 0;  // oldest unreleased chunk
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    auto issue = [&](const uint8_t* src, int rows, int row_bytes, int pitch) {
+        uint32_t seq;
+        const uint32_t bytes = (uint32_t)(rows * pitch);
+        const uint32_t off = R.alloc(bytes, seq);
+        // wait until the region is free and a barrier pair is available (chunks are released in order: wait for
+        // everything up to the newest outstanding chunk that overlaps the new region)
+        uint32_t need = seq >= (uint32_t)kNB ? seq - (uint32_t)kNB + 1u : 0u;
+        for (uint32_t q = q_tail; q < seq; ++q) {
+            const uint32_t o = s_qoff[q % kNB], z = s_qsz[q % kNB];
+            if (!(o + z <= off || off + bytes <= o)) need = q + 1u;
+        }
+        while (q_tail < need) {
+            mbar_wait(&s_empty[q_tail % kNB], (q_tail / kNB) & 1);
+            ++q_tail;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            s_qoff[seq % kNB] = off;
+            s_qsz[seq % kNB] = bytes;
+            mbar_expect_tx(&s_full[seq % kNB], (uint32_t)(rows * row_bytes));
+        }
+        __syncwarp();
+        for (int r = lane; r < rows; r += 32)
+            bulk_g2s_hint(smem_raw + off + (size_t)r * pitch, src + (size_t)r * row_bytes, (uint32_t)row_bytes, &s_full[seq % kNB], pol);
+    };
+    for (int l = 0; l < P.L; ++l) {
+        const LayerDev& Ly = P.layers[l];
+        for (int gt = 2 * a_b0; gt < 2 * a_b1; ++gt) {
+            const int prob = gt / tH, row0 = (gt - prob * tH) * 16;
+            const uint8_t* w = prob == 0 ? Ly.q.w : (prob == 1 ? Ly.k.w : Ly.v.w);
+            issue(w + (size_t)row0 * KbH, 16, KbH, pitchH);
+        }
+        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) issue(Ly.o.w + (size_t)t * 16 * KbH, 16, KbH, pitchH);
+        for (int pb = d_b0; pb < d_b1; ++pb) issue(Ly.gate.w + (size_t)pb * 16 * KbH, 16, KbH, pitchH);
+        for (int pb = d_b0; pb < d_b1; ++pb) issue(Ly.up.w + (size_t)pb * 16 * KbH, 16, KbH, pitchH);
+        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) issue(Ly.down.w + (size_t)t * 16 * KbI, 16, KbI, pitchI);
+    }
+    for (int v = v_b0; v < v_b1; ++v) issue(reinterpret_cast<const uint8_t*>(P.lm_head + (size_t)v * H), 1, 2 * H, 2 * H);
+}
+
+}  // namespace
+
+// ===============================================================================================================
+// the kernel
+// ===============================================================================================================
+__global__ void __launch_bounds__(kThreads, 1)
+step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in, float* __restrict__ logits, int M,
+            int ring_bytes, int dbuf_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[kNB], s_empty[kNB];
+    __shared__ Params P;
+    __shared__ uint32_t s_qoff[kNB], s_qsz[kNB];
+    __shared__ int s_tok[kMaxTok], s_pos[kMaxTok];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(Pg);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&P);
+        for (int i = tid; i < (int)(sizeof(Params) / 4); i += kThreads) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kNB; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int ncta = P.ncta, H = P.H, I = P.I, L = P.L;
+    int a_b0, a_b1, c_b0, c_b1, d_b0, d_b1, v_b0, v_b1;
+    block_range(3 * H / 32, cta, ncta, a_b0, a_b1);   // stage A: 32-row blocks of the [q;k;v] row space
+    block_range(H / 32, cta, ncta, c_b0, c_b1);       // stages C, D2: 32-row blocks of o_proj / down_proj
+    block_range(I / 16, cta, ncta, d_b0, d_b1);       // stage D1: pair blocks (16 gate rows + 16 up rows)
+    block_range(P.V, cta, ncta, v_b0, v_b1);          // lm_head rows
+
+    if (warp == kCW) {
+        producer_loop(P, smem_raw, ring_bytes, s_full, s_empty, s_qoff, s_qsz, lane, a_b0, a_b1, c_b0, c_b1, d_b0, d_b1, v_b0, v_b1);
+        return;
+    }
+
+    // ---- compute warps ----
+    Ctx c;
+    c.tid = tid; c.lane = lane; c.warp = warp; c.cta = cta; c.ncta = ncta; c.M = M; c.H = H; c.I = I; c.pdt = P.pdt;
+    c.ring_bytes = ring_bytes; c.max_batch = P.max_batch;
+    {
+        unsigned char* p = smem_raw;
+        c.S.ring = p; p += ring_bytes;
+        c.S.dbuf = reinterpret_cast<uint32_t*>(p); p += dbuf_bytes;
+        c.S.red = reinterpret_cast<int*>(p); p += kRedBytes;
+        c.S.stat = reinterpret_cast<uint32_t*>(p); p += (size_t)M * ncta * kStatW * 4;
+        c.S.u = reinterpret_cast<float*>(p); p += kMaxTok * 192 * 4;
+        c.S.stage = reinterpret_cast<uint32_t*>(p); p += kMaxTok * 96 * 3 * 4;
+        c.S.redd = reinterpret_cast<double*>(p); p += 32 * 8;
+        c.S.q128 = reinterpret_cast<unsigned long long*>(p); p += 2 * kMaxTok * 8;
+        c.S.invs = reinterpret_cast<double*>(p); p += 2 * kMaxTok * 8;
+        c.S.tile = reinterpret_cast<TileInfo*>(p); p += kMaxTiles * sizeof(TileInfo);
+        c.S.fscr = reinterpret_cast<float*>(p);
+    }
+    c.full = s_full; c.empty = s_empty; c.abort_flag = P.abort_flag;
+    c.R.head = 0; c.R.cap = (uint32_t)ring_bytes; c.R.seq = 0;
+    const unsigned long long step = *P.step_counter;
+    const int par = (int)(step & 1ull);
+    c.X = P.xch[par];
+    c.Xc = P.xch[par ^ 1];
+    c.nownC = 32 * (c_b1 - c_b0); c.colC0 = 32 * c_b0;
+    c.ownerC = c.nownC > 0 && tid < c.nownC * M;
+    c.om = c.ownerC ? tid / c.nownC : 0;
+    c.oc = c.ownerC ? tid - c.om * c.nownC : 0;
+    unsigned long long* trace = P.trace;
+    const bool tracer = cta == 0 && tid == 0;
+    if (tid < kMaxTok) {
+        long long id = tid < M ? ids_in[tid] : 0;
+        id = id < 0 ? 0 : (id >= P.V ? P.V - 1 : id);
+        int ps = tid < M ? P.pos[tid] : 0;
+        if (ps < 0 || ps >= P.max_seq) {  // decoding past the cache: refuse loudly (the host checks first), never overrun
+            atomicExch(P.abort_flag, 2);
+            ps = ps < 0 ? 0 : P.max_seq - 1;
+        }
+        s_tok[tid] = (int)id;
+        s_pos[tid] = ps;
+    }
+    if (tid < 2 * kMaxTok) c.S.q128[tid] = 0ull;
+    cta_sync();
+    if (tracer) trace[0] = gtime();
+
+    float resid = 0.f;
+    // ---- embedding -> residual stream, RMSNorm(input_layernorm of layer 0) -> digits of q/k/v inputs (:1202, :67-81)
+    {
+        float rr[kMaxTok];
+        for (int m = 0; m < M; ++m) {
+            const __half* erow = P.embed + (size_t)s_tok[m] * H;
+            float part = 0.f;
+            for (int i = tid; i < H / 8; i += kCT) {
+                const uint4 raw = reinterpret_cast<const uint4*>(erow)[i];
+                const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __half22float2(h2[q]);
+                    part += f.x * f.x + f.y * f.y;
+                }
+            }
+            const double pd = warp_sum_d((double)part);
+            if (lane == 0) c.S.redd[warp] = pd;
+            cta_sync();
+            double tot = 0.0;
+            for (int w = 0; w < kCW; ++w) tot += c.S.redd[w];
+            rr[m] = rsqrtf((float)(tot / (double)H) + P.rms_eps);
+            cta_sync();
+            if (c.ownerC && c.om == m) resid = __half2float(erow[c.colC0 + c.oc]);
+        }
+        publish_qkv_inputs(c, P, 0, P.layers[0].ln_in, resid, rr);
+    }
+
+    for (int l = 0; l < L; ++l) {
+        const LayerDev& Ly = P.layers[l];
+        const size_t lbase = (size_t)l * P.per_layer;
+        unsigned long long* tr = trace + (size_t)(1 + l) * kTracePoints;
+        if (tracer) tr[0] = gtime();
+        stage_qkv(c, P, l, a_b0, a_b1, s_pos);
+        if (tracer) tr[1] = gtime();
+        stage_attention(c, P, l, s_pos);
+        if (tracer) tr[2] = gtime();
+        {   // stage C: o_proj (:580) + residual + post_attention_layernorm -> digits of gate / up inputs
+            if (tid < kMaxTok) c.S.invs[tid] = pow2d(Ly.e_o - 29);
+            float rr[kMaxTok];
+            residual_stage(c, P, &Ly.o, H, row_pitch(H >> 3), c.X + lbase + P.o_xC, lbase + P.o_cst, &resid, rr);
+            if (c.ownerC) {
+                const int col = c.colC0 + c.oc;
+                const float xh = resid * rr[c.om] * ldp(Ly.ln_post, col, c.pdt);
+                c.S.stage[(size_t)(c.om * 2 + 0) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.gate.h, col, c.pdt), Ly.e_gu[0], col);
+                c.S.stage[(size_t)(c.om * 2 + 1) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.up.h, col, c.pdt), Ly.e_gu[1], col);
+            }
+            cta_sync();
+            publish32(c, lbase + P.o_xD1, (size_t)kMaxTok * H, (size_t)H, 2, c.nownC, c.colC0);
+        }
+        if (tracer) tr[3] = gtime();
+        stage_gate_up(c, P, l, d_b0, d_b1);
+        if (tracer) tr[4] = gtime();
+        {   // stage D2: down_proj (:257) + residual (:918) + the next layer's input_layernorm (or the final norm, :1315)
+            float rr[kMaxTok];
+            residual_stage(c, P, &Ly.down, I, row_pitch(I >> 3), c.X + lbase + P.o_xD2, lbase + P.o_d2st, &resid, rr);
+            if (l + 1 < L) {
+                publish_qkv_inputs(c, P, l + 1, P.layers[l + 1].ln_in, resid, rr);
+            } else {  // final RMSNorm -> fp16 x for lm_head, published as half2 words
+                float* xf = reinterpret_cast<float*>(c.S.stage);
+                if (c.ownerC) xf[c.om * 96 + c.oc] = resid * rr[c.om] * ldp(P.final_norm, c.colC0 + c.oc, c.pdt);
+                cta_sync();
+                const int pairs = c.nownC / 2;
+                uint32_t* Xt = c.X + (size_t)L * P.per_layer;
+                uint32_t* Xtc = c.Xc + (size_t)L * P.per_layer;
+                for (int it = tid; it < kMaxTok * pairs; it += kCT) {
+                    const int m = it / pairs, pc = it - m * pairs;
+                    const size_t a = P.o_xfin + (size_t)m * (H / 2) + (c.colC0 / 2) + pc;
+                    if (m < M) {
+                        const __half2 h2 = __floats2half2_rn(xf[m * 96 + 2 * pc], xf[m * 96 + 2 * pc + 1]);
+                        const uint32_t w = *reinterpret_cast<const uint32_t*>(&h2);
+                        stv1(Xt + a, w == kSentF ? 0x7FFF7FFFu : w);
+                    }
+                    if (m < P.max_batch) stv1(Xtc + a, kSentF);
+                }
+            }
+        }
+        if (tracer) tr[5] = gtime();
+    }
+    unsigned long long* tr = trace + (size_t)(1 + L) * kTracePoints;
+    if (tracer) tr[0] = gtime();
+    stage_lm_head(c, P, v_b0, v_b1, logits, s_pos, step, tr);
+}
+
+}  // namespace persist
+
+// ===================================================================================================================
+// host side
+// ===================================================================================================================
+struct PersistState {
+    persist::Params hp;              // host copy
+    persist::Params* dp = nullptr;   // device copy
+    persist::LayerDev* dlayers = nullptr;
+    uint32_t* xch[2] = {nullptr, nullptr};
+    unsigned long long* step_counter = nullptr;
+    int* abort_flag = nullptr;
+    unsigned long long* trace = nullptr;
+    int ncta = 0;
+    int smem_limit = 0;
+    int trace_words = 0;
+};
+
+namespace {
+
+using namespace persist;
+
+__global__ void fill_words_kernel(uint32_t* p, size_t n, uint32_t v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+float host_param(const void* p, size_t i, int dt) {
+    if (dt == ONEBIT_F16) return __half2float(static_cast<const __half*>(p)[i]);
+    if (dt == ONEBIT_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+    return static_cast<const float*>(p)[i];
+}
+
+int fetch(std::vector<float>& out, const void* dev, size_t n, int dt) {
+    std::vector<unsigned char> raw(n * dtype_size(dt));
+    ONEBIT_CUDA_TRY(cudaMemcpy(raw.data(), dev, raw.size(), cudaMemcpyDeviceToHost));
+    out.resize(n);
+    for (size_t i = 0; i < n; ++i) out[i] = host_param(raw.data(), i, dt);
+    return ONEBIT_OK;
+}
+
+int bound_exp(double b) {  // smallest e with b < 2^e (a little headroom for rounding in the norms)
+    b *= 1.001;
+    if (!(b > 0.0) || !std::isfinite(b)) return 0;
+    int e = 0;
+    std::frexp(b, &e);
+    return e;
+}
+
+size_t round4(size_t w) { return (w + 3) & ~(size_t)3; }
+
+void plan_smem(const Params& P, int M, int smem_limit, Geometry* g) {
+    const int dbuf = (int)std::max<size_t>((size_t)2 * M * P.H * 4, (size_t)M * P.I * 4);
+    const int fixed = kRedBytes + M * P.ncta * kStatW * 4 + kMaxTok * 192 * 4 + kMaxTok * 96 * 3 * 4 + 32 * 8 + 2 * kMaxTok * 8 * 2 +
+                      kMaxTiles * (int)sizeof(TileInfo) + 64 * 4 + 128;
+    g->dbuf_bytes = (dbuf + 127) & ~127;
+    g->ring_bytes = ((smem_limit - 2048 - fixed - g->dbuf_bytes) / 128) * 128;
+    g->smem_bytes = g->ring_bytes + g->dbuf_bytes + fixed;
+}
+
+}  // namespace
+
+bool persist_supported(const onebit_decoder_config& c) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("ONEBIT_PERSIST");
+        env = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!env) return false;
+    const int tp = c.tp_size > 1 ? c.tp_size : 1;
+    if (tp != 1) return false;
+    if (c.max_batch > persist::kMaxTok) return false;
+    if (c.hidden_size % 256 || c.intermediate_size % 256) return false;
+    if (c.hidden_size != c.num_heads * persist::kHeadDim) return false;
+    const int sms = num_sms();
+    if (sms < 64 || (sms & 1)) return false;
+    if (c.num_heads * c.max_batch > sms) return false;
+    // per-CTA tile counts must fit the plan
+    const int a_max = (3 * c.hidden_size / 32 + sms - 1) / sms * 2 + 2, d_max = ((c.intermediate_size / 16 + sms - 1) / sms + 1) * 2;
+    const int c_max = ((c.hidden_size / 32 + sms - 1) / sms) * 2;
+    if (a_max > persist::kMaxTiles + 2 || d_max > persist::kMaxTiles + 2 || c_max > 4) return false;
+    return true;
+}
+
+int persist_create(PersistState** out, const onebit_decoder_config& cfg, const onebit_layer_params* layers, const void* embed,
+                   const void* final_norm, const void* lm_head, const float* rope_cos, const float* rope_sin, __half* kcache,
+                   __half* vcache, long long* ids, int* pos) {
+    *out = nullptr;
+    PersistState* S = new (std::nothrow) PersistState();
+    ONEBIT_REQUIRE(S, "persist_create: out of host memory");
+    Params& P = S->hp;
+    memset(&P, 0, sizeof(P));
+    const int H = cfg.hidden_size, I = cfg.intermediate_size, L = cfg.num_layers, dt = cfg.param_dtype;
+    P.H = H; P.I = I; P.L = L; P.heads = cfg.num_heads; P.V = cfg.vocab_size; P.max_seq = cfg.max_seq_len;
+    P.max_batch = cfg.max_batch; P.pdt = dt; P.ncta = num_sms(); P.rms_eps = cfg.rms_eps; P.ln_eps = cfg.ln_eps;
+    P.inv_H = 1.0 / (double)H; P.inv_I = 1.0 / (double)I;
+    S->ncta = P.ncta;
+    int dev = 0;
+    ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+    ONEBIT_CUDA_TRY(cudaDeviceGetAttribute(&S->smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // exact per-CTA tile bounds
+    for (int c = 0; c < P.ncta; ++c) {
+        auto rng = [&](int nb, int& b0, int& b1) { b0 = (int)((long long)nb * c / P.ncta); b1 = (int)((long long)nb * (c + 1) / P.ncta); };
+        int b0, b1;
+        rng(3 * H / 32, b0, b1);
+        if (2 * (b1 - b0) > kMaxTiles) { delete S; return fail(ONEBIT_ERR_INVALID_ARGUMENT, "persist: too many q/k/v tiles per CTA"); }
+        rng(I / 16, b0, b1);
+        if (2 * (b1 - b0) > kMaxTiles) { delete S; return fail(ONEBIT_ERR_INVALID_ARGUMENT, "persist: too many gate/up tiles per CTA"); }
+        rng(H / 32, b0, b1);
+        if (32 * (b1 - b0) > 96) { delete S; return fail(ONEBIT_ERR_INVALID_ARGUMENT, "persist: too many o/down rows per CTA"); }
+    }
+    // ---- static quantiser bounds from the parameter vectors (host, once)
+    std::vector<LayerDev> hl(L);
+    const double sqH = std::sqrt((double)H);
+    for (int l = 0; l < L; ++l) {
+        const onebit_layer_params& lp = layers[l];
+        LayerDev& d = hl[l];
+        const onebit_bitlinear_params* src[7] = {&lp.q, &lp.k, &lp.v, &lp.o, &lp.gate, &lp.up, &lp.down};
+        BLDev* dst[7] = {&d.q, &d.k, &d.v, &d.o, &d.gate, &d.up, &d.down};
+        for (int i = 0; i < 7; ++i) {
+            dst[i]->w = reinterpret_cast<const uint8_t*>(src[i]->weight);
+            dst[i]->g = src[i]->weight_scale;
+            dst[i]->h = src[i]->input_factor;
+        }
+        d.ln_in = lp.input_layernorm;
+        d.ln_post = lp.post_attention_layernorm;
+        std::vector<float> w_in, w_post, h;
+        int rc = fetch(w_in, lp.input_layernorm, H, dt); if (rc) { delete S; return rc; }
+        rc = fetch(w_post, lp.post_attention_layernorm, H, dt); if (rc) { delete S; return rc; }
+        for (int p = 0; p < 3; ++p) {  // |RMSNorm(x)_k| <= sqrt(H) |w_k|
+            rc = fetch(h, src[p]->input_factor, H, dt); if (rc) { delete S; return rc; }
+            double mx = 0.0;
+            for (int k = 0; k < H; ++k) mx = std::max(mx, std::fabs((double)w_in[k] * (double)h[k]));
+            d.e_qkv[p] = bound_exp(sqH * mx);
+        }
+        {   // attention output: convex combination of LayerNorm outputs, |LN(.)_k| <= sqrt(H)
+            rc = fetch(h, lp.o.input_factor, H, dt); if (rc) { delete S; return rc; }
+            double mx = 0.0;
+            for (int k = 0; k < H; ++k) mx = std::max(mx, std::fabs((double)h[k]));
+            d.e_o = bound_exp(sqH * mx);
+        }
+        for (int p = 0; p < 2; ++p) {
+            rc = fetch(h, src[4 + p]->input_factor, H, dt); if (rc) { delete S; return rc; }
+            double mx = 0.0;
+            for (int k = 0; k < H; ++k) mx = std::max(mx, std::fabs((double)w_post[k] * (double)h[k]));
+            d.e_gu[p] = bound_exp(sqH * mx);
+        }
+        {
+            rc = fetch(h, lp.down.input_factor, I, dt); if (rc) { delete S; return rc; }
+            double mx = 0.0;
+            for (int k = 0; k < I; ++k) mx = std::max(mx, std::fabs((double)h[k]));
+            d.hmax_down = (float)mx;
+        }
+    }
+    // ---- exchange arenas
+    const size_t B = kMaxTok, nc = P.ncta;
+    size_t o = 0;
+    P.o_xA = o; o += round4(3 * B * H);
+    P.o_qkv = o; o += round4(B * 3 * H);
+    P.o_qst = o; o += round4(B * 3 * nc * 4);
+    P.o_xC = o; o += round4(B * H);
+    P.o_cst = o; o += round4(B * nc * kStatW);
+    P.o_xD1 = o; o += round4(2 * B * H);
+    P.o_dst = o; o += round4(B * nc * kStatW);
+    P.o_xD2 = o; o += round4(B * I);
+    P.o_d2st = o; o += round4(B * nc * kStatW);
+    P.per_layer = o;
+    size_t t = 0;
+    P.o_xfin = t; t += round4(B * (H / 2));
+    P.o_amax = t; t += round4(B * nc * 2);
+    P.total_words = P.per_layer * L + t;
+    auto cleanup = [&]() { persist_destroy(S); };
+    for (int s = 0; s < 2; ++s) {
+        cudaError_t e = cudaMalloc(&S->xch[s], P.total_words * 4);
+        if (e != cudaSuccess) { cleanup(); return fail(ONEBIT_ERR_CUDA, std::string("persist_create: cudaMalloc: ") + cudaGetErrorString(e)); }
+        P.xch[s] = S->xch[s];
+        // sentinels: digit regions 0x80808080, everything else 0xFFFFFFFF
+        fill_words_kernel<<<256, 256>>>(S->xch[s], P.total_words, kSentF);
+        for (int l = 0; l < L; ++l) {
+            uint32_t* base = S->xch[s] + (size_t)l * P.per_layer;
+            fill_words_kernel<<<64, 256>>>(base + P.o_xA, 3 * B * H, kSentD);
+            fill_words_kernel<<<64, 256>>>(base + P.o_xC, B * H, kSentD);
+            fill_words_kernel<<<64, 256>>>(base + P.o_xD1, 2 * B * H, kSentD);
+            fill_words_kernel<<<64, 256>>>(base + P.o_xD2, B * I, kSentD);
+        }
+    }
+    S->trace_words = kTracePoints * (L + 2);
+    if (cudaMalloc(&S->dlayers, sizeof(LayerDev) * L) != cudaSuccess || cudaMalloc(&S->dp, sizeof(Params)) != cudaSuccess ||
+        cudaMalloc(&S->step_counter, 8) != cudaSuccess || cudaMalloc(&S->abort_flag, 4) != cudaSuccess ||
+        cudaMalloc(&S->trace, sizeof(unsigned long long) * S->trace_words) != cudaSuccess) {
+        cleanup();
+        return fail(ONEBIT_ERR_CUDA, "persist_create: cudaMalloc failed");
+    }
+    cudaMemset(S->step_counter, 0, 8);
+    cudaMemset(S->abort_flag, 0, 4);
+    cudaMemset(S->trace, 0, sizeof(unsigned long long) * S->trace_words);
+    cudaMemcpy(S->dlayers, hl.data(), sizeof(LayerDev) * L, cudaMemcpyHostToDevice);
+    P.layers = S->dlayers;
+    P.embed = static_cast<const __half*>(embed);
+    P.final_norm = final_norm;
+    P.lm_head = static_cast<const __half*>(lm_head);
+    P.rope_cos = rope_cos; P.rope_sin = rope_sin;
+    P.kcache = kcache; P.vcache = vcache;
+    P.step_counter = S->step_counter; P.abort_flag = S->abort_flag; P.trace = S->trace;
+    P.ids = ids; P.pos = pos;
+    cudaMemcpy(S->dp, &P, sizeof(Params), cudaMemcpyHostToDevice);
+    ONEBIT_CUDA_TRY(cudaFuncSetAttribute(persist::step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S->smem_limit - 2048));
+    {
+        Geometry g;
+        plan_smem(P, cfg.max_batch, S->smem_limit, &g);
+        const int need = 16 * row_pitch(I / 8);  // the ring must hold at least the two down_proj tiles + slack
+        if (g.ring_bytes < 4 * need) { cleanup(); return fail(ONEBIT_ERR_INVALID_ARGUMENT, "persist_create: model too wide for the shared-memory ring"); }
+    }
+    ONEBIT_CUDA_TRY(cudaDeviceSynchronize());
+    *out = S;
+    return ONEBIT_OK;
+}
+
+int persist_step(PersistState* S, int batch, const long long* ids_in, float* logits, cudaStream_t s) {
+    ONEBIT_REQUIRE(S && batch >= 1 && batch <= kMaxTok && batch <= S->hp.max_batch, "persist_step: bad batch");
+    Geometry g;
+    plan_smem(S->hp, batch, S->smem_limit, &g);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)S->ncta);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)g.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait on each other's data
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const Params* dp = S->dp;
+    ONEBIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, persist::step_kernel, dp, ids_in, logits, batch, g.ring_bytes, g.dbuf_bytes));
+    return ONEBIT_OK;
+}
+
+int persist_read_trace(PersistState* S, unsigned long long* out, int n) {
+    ONEBIT_REQUIRE(S && out && n > 0, "persist_read_trace: bad arguments");
+    const int m = std::min(n, S->trace_words);
+    ONEBIT_CUDA_TRY(cudaMemcpy(out, S->trace, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost));
+    return m;
+}
+
+int persist_abort_flag(PersistState* S, int* out) {
+    ONEBIT_REQUIRE(S && out, "persist_abort_flag: bad arguments");
+    ONEBIT_CUDA_TRY(cudaMemcpy(out, S->abort_flag, 4, cudaMemcpyDeviceToHost));
+    return ONEBIT_OK;
+}
+
+void persist_destroy(PersistState* S) {
+    if (!S) return;
+    cudaFree(S->xch[0]);
+    cudaFree(S->xch[1]);
+    cudaFree(S->dlayers);
+    cudaFree(S->dp);
+    cudaFree(S->step_counter);
+    cudaFree(S->abort_flag);
+    cudaFree(S->trace);
+    delete S;
+}
+
+}  // namespace onebit

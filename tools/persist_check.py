@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""Bring-up / regression tool for the persistent decode step (run on the GPU box):
+    python tools/persist_check.py tiny|wide7b|wide13b|time7b|time13b [...]
+Each section prints one JSON line. Sections are independent; run each under `timeout`."""
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from onebit_b200 import LLAMA2_13B, LLAMA_7B, BitLlamaDecoderB200, synthetic_state_dict  # noqa: E402
+from oracle import oracle, ref_port  # noqa: E402
+
+
+def load_tiny():
+    z = np.load(ROOT / "tests" / "golden" / "tiny_model.npz")
+    cfg = {k: v for k, v in zip(z["config_keys"], z["config_vals"])}
+    config = {k: (float(cfg[k]) if k in ("rms_norm_eps", "rope_theta") else int(cfg[k]))
+              for k in ("hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "vocab_size",
+                        "rms_norm_eps", "rope_theta")}
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    return config, sd, z
+
+
+def sec_tiny():
+    config, sd, z = load_tiny()
+    out = {"section": "tiny"}
+    for pd, nm in ((torch.float32, "f32"), (torch.float16, "f16")):
+        dec = BitLlamaDecoderB200(config, sd, max_seq_len=256, max_batch=2, param_dtype=pd, use_graph=(pd == torch.float16))
+        ids = torch.from_numpy(z["input_ids"])
+        logits = dec.forward_tokens(ids).cpu().numpy()
+        out[f"persistent_{nm}"] = dec.persistent
+        out[f"status_{nm}"] = dec.status()
+        out[f"logits_rel_l2_{nm}"] = float(oracle.rel_l2(logits, z["logits"]))
+        out[f"finite_{nm}"] = bool(np.isfinite(logits).all())
+        ppl = dec.perplexity(ids)
+        out[f"ppl_{nm}"] = ppl
+        out["ppl_ref"] = float(z["ppl"])
+        prompt = torch.from_numpy(z["prompt"])
+        want = z["generated"]
+        got = dec.generate(prompt, max_new_tokens=want.shape[1] - prompt.shape[1]).cpu().numpy()
+        out[f"greedy_agree_{nm}"] = float((got == want).mean())
+        # batch 1 must equal row 0 of batch 2 bit for bit
+        d1 = BitLlamaDecoderB200(config, sd, max_seq_len=256, max_batch=1, param_dtype=pd, use_graph=False)
+        a = d1.forward_tokens(ids[:1, :16])
+        b = dec.forward_tokens(ids[:, :16])
+        out[f"batch_invariant_{nm}"] = bool(torch.equal(a[0], b[0]))
+        d1.close()
+        dec.close()
+    print(json.dumps(out), flush=True)
+
+
+def wide(config, name, layers, tokens, batch=1):
+    config = dict(config, num_hidden_layers=layers)
+    sd = synthetic_state_dict(config, seed=3, param_dtype=torch.float32)
+    gen = torch.Generator().manual_seed(5)
+    ids = torch.randint(3, config["vocab_size"], (batch, tokens), generator=gen)
+    model = ref_port.RefPortModel(config, sd)
+    t0 = time.time()
+    with torch.no_grad():
+        want, _ = model.forward(ids)
+    t_ref = time.time() - t0
+    out = {"section": name, "layers": layers, "tokens": tokens, "batch": batch, "ref_s": t_ref}
+    for pd, nm in ((torch.float32, "f32"), (torch.float16, "f16")):
+        dec = BitLlamaDecoderB200(config, sd, max_seq_len=64, max_batch=batch, param_dtype=pd)
+        got = dec.forward_tokens(ids).cpu().numpy()
+        out[f"persistent_{nm}"] = dec.persistent
+        out[f"status_{nm}"] = dec.status()
+        out[f"logits_rel_l2_{nm}"] = float(oracle.rel_l2(got, want.numpy()))
+        out[f"argmax_agree_{nm}"] = float((got.argmax(-1) == want.numpy().argmax(-1)).mean())
+        dec.close()
+    print(json.dumps(out), flush=True)
+
+
+def timing(config, name, batch=1, steps=64, prompt_len=16):
+    sd = synthetic_state_dict(config, seed=0)
+    dec = BitLlamaDecoderB200(config, sd, max_seq_len=prompt_len + steps * 3 + 64, max_batch=batch)
+    del sd
+    gen = torch.Generator().manual_seed(1234)
+    prompt = torch.randint(3, config["vocab_size"], (batch, prompt_len), generator=gen)
+    dec.reset(prompt[:, 0])
+    ids = prompt.cuda()
+    for i in range(prompt_len):
+        dec.step(ids[:, i])
+    for _ in range(8):
+        dec.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        dec.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"section": name, "batch": batch, "ms_per_step": ms, "tok_s": batch * 1e3 / ms, "persistent": dec.persistent,
+           "status": dec.status(), "launches": dec.launches_per_step()}
+    tr = dec.read_trace()
+    if tr is not None:
+        L = dec.L
+        t = tr.astype(np.int64)
+        lay = t[1:1 + L]
+        seg = np.diff(lay[:, :6], axis=1)  # qkv, attention, o+resid, gate/up, down+resid
+        out["trace_us"] = {"embed": float(lay[0, 0] - t[0, 0]) / 1e3,
+                           "per_layer_mean": [float(x) / 1e3 for x in seg.mean(0)],
+                           "per_layer_first": [float(x) / 1e3 for x in seg[0]],
+                           "per_layer_last": [float(x) / 1e3 for x in seg[-1]],
+                           "layers_total": float(lay[-1, 5] - lay[0, 0]) / 1e3,
+                           "lm_head": float(t[1 + L, 1] - t[1 + L, 0]) / 1e3,
+                           "kernel_total": float(t[1 + L, 1] - t[0, 0]) / 1e3}
+    dec.close()
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    for arg in sys.argv[1:]:
+        if arg == "tiny":
+            sec_tiny()
+        elif arg == "wide7b":
+            wide(LLAMA_7B, "wide7b", 2, 6)
+        elif arg == "wide7b_b2":
+            wide(LLAMA_7B, "wide7b_b2", 2, 4, batch=2)
+        elif arg == "wide13b":
+            wide(LLAMA2_13B, "wide13b", 1, 4)
+        elif arg == "time7b":
+            timing(LLAMA_7B, "time7b")
+        elif arg == "time7b_b2":
+            timing(LLAMA_7B, "time7b_b2", batch=2)
+        elif arg == "time13b":
+            timing(LLAMA2_13B, "time13b")
+        else:
+            raise SystemExit(f"unknown section {arg}")
