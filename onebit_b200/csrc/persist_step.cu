@@ -63,18 +63,33 @@ __device__ __forceinline__ uint32_t fbits(float f) {  // publishable bit pattern
     return b == kSentF ? 0x7FFFFFFFu : b;
 }
 
-// give-up logic of every polling loop: a protocol bug must end the kernel, not hang the GPU
+// give-up logic of every polling loop: a protocol bug must end the kernel, not hang the GPU. The bound is a
+// wall-clock deadline for the whole step (set by every CTA at kernel start), checked every 1024 failed polls.
+__shared__ unsigned long long s_deadline;
+constexpr unsigned long long kStepBudgetNs = 400ull * 1000ull * 1000ull;
 __device__ __noinline__ bool spin_giveup_slow(int spins, int* abort_flag) {
     if (ldv1(reinterpret_cast<const uint32_t*>(abort_flag)) != 0u) return true;
-    if (spins > (1 << 21)) {
+    if (spins >= 1024 && gtime() > s_deadline) {
         atomicExch(abort_flag, 1);
         return true;
     }
     return false;
 }
 __device__ __forceinline__ bool spin_giveup(int& spins, int* abort_flag) {
-    if ((++spins & 1023) != 0) return false;
+    ++spins;
+    if (spins != 8 && (spins & 1023) != 0) return false;  // the check at 8 makes an aborted step drain quickly
     return spin_giveup_slow(spins, abort_flag);
+}
+// bounded mbarrier wait (a lost TMA completion must end the kernel, not hang the GPU); false = gave up
+__device__ __noinline__ bool mbar_wait_b(uint64_t* bar, uint32_t parity, int* abort_flag) {
+    int spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+        if (spin_giveup(spins, abort_flag)) return false;
+    }
 }
 
 __device__ __forceinline__ size_t dsize(int pdt) { return pdt == ONEBIT_F32 ? 4 : 2; }
@@ -352,7 +367,7 @@ __device__ __noinline__ void stage_core(Ctx& c, int K, int pitch, int T, uint32_
         const int n = min(psz, T - p0);
         if (c.warp < n && c.lane == 0) {
             const uint32_t sq = seq0 + (uint32_t)(p0 + c.warp);
-            mbar_wait(&c.full[sq % kNB], (sq / kNB) & 1);
+            mbar_wait_b(&c.full[sq % kNB], (sq / kNB) & 1, c.abort_flag);
         }
         cta_sync();
         imma_phase(c.S.ring, c.S.tile, p0, n, K, pitch, c.S.dbuf, set_words, c.M, c.S.red, c.warp, c.lane);
@@ -819,7 +834,7 @@ __device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, in
         uint32_t seq;
         const uint32_t off = c.R.alloc((uint32_t)(2 * H), seq);
         if ((int)(seq % kCW) != warp) continue;
-        mbar_wait(&c.full[seq % kNB], (seq / kNB) & 1);
+        mbar_wait_b(&c.full[seq % kNB], (seq / kNB) & 1, c.abort_flag);
         const uint4* wr = reinterpret_cast<const uint4*>(c.S.ring + off);
         float acc[kMaxTok] = {0.f, 0.f};
         for (int i = lane; i < nch; i += 32) {
@@ -905,7 +920,7 @@ __device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_
     uint32_t q_tail = 0;  // oldest unreleased chunk
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    auto issue = [&](const uint8_t* src, int rows, int row_bytes, int pitch) {
+    auto issue = [&](const uint8_t* src, int rows, int row_bytes, int pitch) -> bool {
         uint32_t seq;
         const uint32_t bytes = (uint32_t)(rows * pitch);
         const uint32_t off = R.alloc(bytes, seq);
@@ -917,7 +932,7 @@ __device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_
             if (!(o + z <= off || off + bytes <= o)) need = q + 1u;
         }
         while (q_tail < need) {
-            mbar_wait(&s_empty[q_tail % kNB], (q_tail / kNB) & 1);
+            if (!mbar_wait_b(&s_empty[q_tail % kNB], (q_tail / kNB) & 1, P.abort_flag)) return false;
             ++q_tail;
         }
         __syncwarp();
@@ -929,20 +944,21 @@ __device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_
         __syncwarp();
         for (int r = lane; r < rows; r += 32)
             bulk_g2s_hint(smem_raw + off + (size_t)r * pitch, src + (size_t)r * row_bytes, (uint32_t)row_bytes, &s_full[seq % kNB], pol);
+        return true;
     };
     for (int l = 0; l < P.L; ++l) {
         const LayerDev& Ly = P.layers[l];
         for (int gt = 2 * a_b0; gt < 2 * a_b1; ++gt) {
             const int prob = gt / tH, row0 = (gt - prob * tH) * 16;
             const uint8_t* w = prob == 0 ? Ly.q.w : (prob == 1 ? Ly.k.w : Ly.v.w);
-            issue(w + (size_t)row0 * KbH, 16, KbH, pitchH);
+            if (!issue(w + (size_t)row0 * KbH, 16, KbH, pitchH)) return;
         }
-        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) issue(Ly.o.w + (size_t)t * 16 * KbH, 16, KbH, pitchH);
-        for (int pb = d_b0; pb < d_b1; ++pb) issue(Ly.gate.w + (size_t)pb * 16 * KbH, 16, KbH, pitchH);
-        for (int pb = d_b0; pb < d_b1; ++pb) issue(Ly.up.w + (size_t)pb * 16 * KbH, 16, KbH, pitchH);
-        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) issue(Ly.down.w + (size_t)t * 16 * KbI, 16, KbI, pitchI);
+        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.o.w + (size_t)t * 16 * KbH, 16, KbH, pitchH)) return;
+        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.gate.w + (size_t)pb * 16 * KbH, 16, KbH, pitchH)) return;
+        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.up.w + (size_t)pb * 16 * KbH, 16, KbH, pitchH)) return;
+        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.down.w + (size_t)t * 16 * KbI, 16, KbI, pitchI)) return;
     }
-    for (int v = v_b0; v < v_b1; ++v) issue(reinterpret_cast<const uint8_t*>(P.lm_head + (size_t)v * H), 1, 2 * H, 2 * H);
+    for (int v = v_b0; v < v_b1; ++v) if (!issue(reinterpret_cast<const uint8_t*>(P.lm_head + (size_t)v * H), 1, 2 * H, 2 * H)) return;
 }
 
 }  // namespace
@@ -967,6 +983,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         for (int i = tid; i < (int)(sizeof(Params) / 4); i += kThreads) dst[i] = src[i];
     }
     if (tid == 0) {
+        s_deadline = gtime() + kStepBudgetNs;
         for (int i = 0; i < kNB; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 1);

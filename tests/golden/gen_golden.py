@@ -218,6 +218,36 @@ def gen_model():
     print("tiny_model.npz ppl", ppl.item(), "generated", gen.shape)
 
 
+def gen_ppl512():
+    """A fixed 512-token slice for the perplexity-parity gate (north_star: "perplexity on a fixed 512-token slice
+    matches to 3 decimals"). The slice is SAMPLED from the tiny reference model itself (temperature 0.1), so
+    the perplexity is in the range of a trained model instead of ~vocab_size; the number stored is the reference's:
+    evaluation/lm_eval.py:99-124 on one 512-token window, fp32 on CPU. Weights are those of tiny_model.npz."""
+    BitLlamaConfig, BitLlamaForCausalLMInf = import_reference_transformers()
+    z = np.load(HERE / "tiny_model.npz")
+    cfg = BitLlamaConfig(**dict(TINY, max_position_embeddings=512))
+    model = BitLlamaForCausalLMInf(cfg).float().eval()
+    model.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")})
+    torch.manual_seed(20240917)
+    seqlen = 512
+    prompt = torch.tensor([[1, 17, 230, 5]], dtype=torch.int64)
+    with torch.no_grad():
+        ids = model.generate(prompt, max_new_tokens=seqlen - prompt.shape[1], do_sample=True, temperature=0.1, top_k=0,
+                             eos_token_id=None, pad_token_id=0)
+        assert ids.shape == (1, seqlen)
+        hs = model.model(ids)[0]
+        lg = model.lm_head(hs)
+        loss = torch.nn.CrossEntropyLoss()(lg[:, :-1, :].reshape(-1, lg.size(-1)), ids[:, 1:].reshape(-1))
+        nll = loss.float() * seqlen
+        ppl = torch.exp(nll / seqlen)
+        # the same quantity accumulated in float64 from the fp32 logits (what the parity test recomputes)
+        loss64 = torch.nn.functional.cross_entropy(lg[0, :-1].double(), ids[0, 1:])
+        ppl64 = torch.exp(loss64 * seqlen / seqlen)
+    np.savez_compressed(HERE / "tiny_ppl512.npz", input_ids=ids.numpy(), ppl=np.float64(ppl.item()), ppl64=np.float64(ppl64.item()),
+                        last_logits=lg[0, -1].float().numpy(), logits_stride64=lg[0, ::64].float().numpy())
+    print("tiny_ppl512.npz ppl", ppl.item(), "ppl64", ppl64.item())
+
+
 def gen_rope():
     """cos/sin caches of the reference's LlamaRotaryEmbedding (modeling_bitllama.py:87-121), head_dim 128."""
     import_reference_transformers()
@@ -230,7 +260,7 @@ def gen_rope():
 
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
-    which = set(sys.argv[1:]) or {"pack", "forward", "equiv", "model", "rope"}
+    which = set(sys.argv[1:]) or {"pack", "forward", "equiv", "model", "rope", "ppl512"}
     bitnet = load_bitnet()
     packer = load_packer()
     if "pack" in which:
@@ -243,3 +273,5 @@ if __name__ == "__main__":
         gen_model()
     if "rope" in which:
         gen_rope()
+    if "ppl512" in which:
+        gen_ppl512()

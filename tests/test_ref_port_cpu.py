@@ -45,3 +45,20 @@ def test_port_bitlinear_matches_c_oracle():
                                      torch.from_numpy(case["bias"])).numpy()
     want = oracle.bitlinear_forward_c(case["x"], case["packed"], case["g"], case["h"], case["bias"])
     assert oracle.rel_l2(got, want) < 2e-6
+
+
+def test_port_reproduces_the_512_token_perplexity_fixture(golden_dir):
+    """tests/golden/tiny_ppl512.npz: evaluation/lm_eval.py:99-124 on one fixed 512-token window, produced by the
+    reference's own BitLlamaForCausalLMInf. The port must land on the same number to 3 decimals."""
+    config, sd, _ = _load(golden_dir)
+    z = np.load(golden_dir / "tiny_ppl512.npz")
+    ids = torch.from_numpy(z["input_ids"])
+    assert ids.shape == (1, 512)
+    model = ref_port.RefPortModel(config, sd)
+    with torch.no_grad():
+        logits, _ = model.forward(ids)
+    loss = torch.nn.functional.cross_entropy(logits[0, :-1].double(), ids[0, 1:])
+    ppl = float(torch.exp(loss))
+    assert abs(ppl - float(z["ppl64"])) < 5e-4
+    assert abs(ppl - float(z["ppl"])) < 5e-4
+    assert oracle.rel_l2(logits[0, -1].numpy(), z["last_logits"]) < 1e-5
