@@ -66,6 +66,7 @@ __device__ __forceinline__ uint32_t fbits(float f) {  // publishable bit pattern
 // give-up logic of every polling loop: a protocol bug must end the kernel, not hang the GPU. The bound is a
 // wall-clock deadline for the whole step (set by every CTA at kernel start), checked every 1024 failed polls.
 __shared__ unsigned long long s_deadline;
+constexpr int kLmRows = 2;  // lm_head rows per ring chunk
 constexpr unsigned long long kStepBudgetNs = 400ull * 1000ull * 1000ull;
 __device__ __noinline__ bool spin_giveup_slow(int spins, int* abort_flag) {
     if (ldv1(reinterpret_cast<const uint32_t*>(abort_flag)) != 0u) return true;
@@ -209,7 +210,11 @@ struct Ctx {
     uint32_t* X;   // this step's exchange arena
     uint32_t* Xc;  // the other parity set: re-armed (sentinels) word for word as we publish
     Ring R;
+    unsigned long long* trl;  // trace row of the current layer (tracer CTAs only, else nullptr)
 };
+__device__ __forceinline__ void stamp(const Ctx& c, int slot) {
+    if (c.trl != nullptr && c.tid == 0) c.trl[slot] = gtime();
+}
 
 // ---- Lamport copies global -> shared ------------------------------------------------------------------------
 // digit vector of K words: also commits this vector's Q128 = 128 * sum_k q_k to *q128 (integer, order independent)
@@ -354,14 +359,16 @@ __device__ __noinline__ void put_tile(Ctx& c, int i, int T, int pitch, uint32_t 
 
 // generic BitLinear stage core: copy the input digit vectors (Lamport poll), run the IMMA passes, release the tiles.
 // `seq0`: ring sequence number of the stage's first tile (its T tiles are consecutive chunks).
-__device__ __noinline__ void stage_core(Ctx& c, int K, int pitch, int T, uint32_t seq0, int nsets, const uint32_t* x0, const uint32_t* x1) {
+__device__ __noinline__ void stage_core(Ctx& c, int K, int pitch, int T, uint32_t seq0, int nsets, const uint32_t* x0, const uint32_t* x1, int ts) {
     const int set_words = c.M * K;
+    cta_sync();  // S.tile / S.invs / S.q128 of this stage are in place, the previous stage's readers are done
     if (T > 0) {
         for (int ps = 0; ps < nsets; ++ps)
             for (int m = 0; m < c.M; ++m)
                 poll_copy_d((ps ? x1 : x0) + (size_t)m * K, c.S.dbuf + (size_t)ps * set_words + (size_t)m * K, K / 4, c.tid, c.lane,
                             &c.S.q128[ps * kMaxTok + m], c.abort_flag);
     }
+    stamp(c, ts);
     const int psz = pass_size(T, 16 * pitch, c.ring_bytes);
     for (int p0 = 0; p0 < max(T, 1); p0 += psz) {
         const int n = min(psz, T - p0);
@@ -374,6 +381,7 @@ __device__ __noinline__ void stage_core(Ctx& c, int K, int pitch, int T, uint32_
         cta_sync();
         if (c.tid < n) mbar_arrive(&c.empty[(seq0 + (uint32_t)(p0 + c.tid)) % kNB]);
     }
+    stamp(c, ts + 1);
 }
 
 // publish the digits of `nprob` BitLinear inputs for the owned 32-column blocks: S.stage[(m*nprob+p)*nown + col] holds
@@ -458,7 +466,7 @@ __device__ __noinline__ void publish_qkv_inputs(Ctx& c, const Params& P, int l, 
 // x <- x + LayerNorm(g*t) (:912 / :918) and the RMSNorm factor of the next BitLinear group (:67-81), all from ONE
 // exchange of five per-CTA sums (sum u, sum u^2, sum r, sum r^2, sum r*u).
 __device__ __noinline__ void residual_stage(Ctx& c, const Params& P, const BLDev* bl, int K, int pitch, const uint32_t* xin0, size_t o_stat,
-                                            float* resid_io, float* rr_out /*[M]*/) {
+                                            float* resid_io, float* rr_out /*[M]*/, int ts) {
     const int T = c.nownC >> 4;
     const uint32_t seq0 = c.R.seq;
     for (int i = 0; i < T; ++i) {
@@ -466,7 +474,7 @@ __device__ __noinline__ void residual_stage(Ctx& c, const Params& P, const BLDev
         const uint32_t off = c.R.alloc(16u * pitch, seq);
         if (c.tid == i) put_tile(c, i, T, pitch, off, 0, bl->g, c.colC0 + 16 * i);
     }
-    stage_core(c, K, pitch, T, seq0, 1, xin0, xin0);
+    stage_core(c, K, pitch, T, seq0, 1, xin0, xin0, ts);
     float u = 0.f, resid = *resid_io;
     if (c.ownerC) {
         const TileInfo* ti = &c.S.tile[c.oc >> 4];
@@ -499,6 +507,7 @@ __device__ __noinline__ void residual_stage(Ctx& c, const Params& P, const BLDev
         }
     }
     stats_exchange(c, o_stat, 5, 0);
+    stamp(c, ts + 2);
     if (c.tid < c.M) {  // one thread per token: LayerNorm statistics and the RMSNorm factor of the updated stream
         const double* rd = c.S.redd + c.tid * 5;
         const double N = (double)c.H;
@@ -545,7 +554,7 @@ __device__ __noinline__ void stage_qkv(Ctx& c, const Params& P, int l, int a_b0,
             prefetch_l2(reinterpret_cast<const char*>(P.vcache + base) + (size_t)i * 128);
         }
     }
-    stage_core(c, H, pitchH, T, seq0, nsets, XL + P.o_xA + (size_t)p_lo * kMaxTok * H, XL + P.o_xA + (size_t)min(p_lo + 1, 2) * kMaxTok * H);
+    stage_core(c, H, pitchH, T, seq0, nsets, XL + P.o_xA + (size_t)p_lo * kMaxTok * H, XL + P.o_xA + (size_t)min(p_lo + 1, 2) * kMaxTok * H, 6);
     const int Rr = 16 * T;
     if (c.tid < Rr * kMaxTok) {
         const int em = c.tid / Rr, er = c.tid - em * Rr;
@@ -629,6 +638,7 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
         if (lane == 0) c.S.redd[warp] = s;
     }
     cta_sync();
+    stamp(c, 17);
     if (tid < 3) ln_finish(c.S.redd[2 * tid], c.S.redd[2 * tid + 1], P.inv_H, P.ln_eps, &c.S.fscr[2 * tid], &c.S.fscr[2 * tid + 1]);
     cta_sync();
     __half* kc = P.kcache + ((((size_t)l * P.max_batch + am) * P.heads + ah) * P.max_seq) * kHeadDim;
@@ -650,6 +660,7 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
         sv[d] = __half2float(vh);
     }
     cta_sync();
+    stamp(c, 18);
     {   // each warp: online softmax over positions warp, warp+16, ...; lane holds dims 4*lane .. 4*lane+3
         const float4 qv = *reinterpret_cast<const float4*>(sq + 4 * lane);
         float mx = -INFINITY, lsum = 0.f;
@@ -698,6 +709,7 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
         *reinterpret_cast<float4*>(pw + 4 + 4 * lane) = o;
     }
     cta_sync();
+    stamp(c, 19);
     if (tid < kHeadDim) {
         float mx = -INFINITY;
         for (int w = 0; w < kCW; ++w) mx = fmaxf(mx, part[w * 132]);
@@ -742,7 +754,7 @@ __device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d
         }
     }
     if (tid < 2 * kMaxTok) c.S.invs[tid] = pow2d(Ly.e_gu[tid / kMaxTok] - 29);
-    stage_core(c, H, pitchH, T, seq0, 2, XL + P.o_xD1, XL + P.o_xD1 + (size_t)kMaxTok * H);
+    stage_core(c, H, pitchH, T, seq0, 2, XL + P.o_xD1, XL + P.o_xD1 + (size_t)kMaxTok * H, 11);
     const int Rr = 16 * T;
     if (Rr > 0) {
         const int em = tid / Rr, er = tid - em * Rr;
@@ -790,6 +802,7 @@ __device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d
         }
     }
     stats_exchange(c, (size_t)l * P.per_layer + P.o_dst, 4, 3);
+    stamp(c, 13);
     if (tid < c.M) {  // per token: LayerNorm statistics of gate and up, power-of-two bound of down_proj's input
         const double* rd = c.S.redd + tid * 7;
         float mg, rg, mu, ru;
@@ -830,25 +843,38 @@ __device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, in
 #pragma unroll
     for (int m = 0; m < kMaxTok; ++m) { best[m] = -INFINITY; bidx[m] = 0x7fffffff; }
     const int nch = H / 8;  // uint4 chunks per row
-    for (int v = v_b0; v < v_b1; ++v) {
+    for (int v0 = v_b0; v0 < v_b1; v0 += kLmRows) {
+        const int nr = min(kLmRows, v_b1 - v0);
         uint32_t seq;
-        const uint32_t off = c.R.alloc((uint32_t)(2 * H), seq);
+        const uint32_t off = c.R.alloc((uint32_t)(nr * 2 * H), seq);
         if ((int)(seq % kCW) != warp) continue;
         mbar_wait_b(&c.full[seq % kNB], (seq / kNB) & 1, c.abort_flag);
+        float acc[kLmRows][kMaxTok];
+#pragma unroll
+        for (int r = 0; r < kLmRows; ++r)
+#pragma unroll
+            for (int m = 0; m < kMaxTok; ++m) acc[r][m] = 0.f;
         const uint4* wr = reinterpret_cast<const uint4*>(c.S.ring + off);
-        float acc[kMaxTok] = {0.f, 0.f};
         for (int i = lane; i < nch; i += 32) {
-            const uint4 wv = wr[i];
-            const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
+            uint4 xv[kMaxTok];
 #pragma unroll
-            for (int m = 0; m < kMaxTok; ++m) {
-                if (m < M) {
-                    const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)m * (H / 2))[i];
-                    const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
+            for (int m = 0; m < kMaxTok; ++m)
+                xv[m] = m < M ? reinterpret_cast<const uint4*>(xs + (size_t)m * (H / 2))[i] : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float2 a = __half22float2(w2[q]), b = __half22float2(x2[q]);
-                        acc[m] += a.x * b.x + a.y * b.y;
+            for (int r = 0; r < kLmRows; ++r) {
+                if (r < nr) {
+                    const uint4 wv = wr[r * nch + i];
+                    const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+                    for (int m = 0; m < kMaxTok; ++m) {
+                        if (m < M) {
+                            const __half2* x2 = reinterpret_cast<const __half2*>(&xv[m]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 a = __half22float2(w2[q]), b = __half22float2(x2[q]);
+                                acc[r][m] += a.x * b.x + a.y * b.y;
+                            }
+                        }
                     }
                 }
             }
@@ -856,11 +882,17 @@ __device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, in
         __syncwarp();
         if (lane == 0) mbar_arrive(&c.empty[seq % kNB]);
 #pragma unroll
-        for (int m = 0; m < kMaxTok; ++m) {
-            if (m < M) {
-                const float r = warp_sum(acc[m]);
-                if (lane == 0) logits[(size_t)m * P.V + v] = r;
-                if (r > best[m] || (r == best[m] && v < bidx[m])) { best[m] = r; bidx[m] = v; }
+        for (int r = 0; r < kLmRows; ++r) {
+            if (r < nr) {
+                const int v = v0 + r;
+#pragma unroll
+                for (int m = 0; m < kMaxTok; ++m) {
+                    if (m < M) {
+                        const float rs = warp_sum(acc[r][m]);
+                        if (lane == 0) logits[(size_t)m * P.V + v] = rs;
+                        if (rs > best[m] || (rs == best[m] && v < bidx[m])) { best[m] = rs; bidx[m] = v; }
+                    }
+                }
             }
         }
     }
@@ -924,14 +956,16 @@ __device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_
         uint32_t seq;
         const uint32_t bytes = (uint32_t)(rows * pitch);
         const uint32_t off = R.alloc(bytes, seq);
-        // wait until the region is free and a barrier pair is available (chunks are released in order: wait for
-        // everything up to the newest outstanding chunk that overlaps the new region)
-        uint32_t need = seq >= (uint32_t)kNB ? seq - (uint32_t)kNB + 1u : 0u;
-        for (uint32_t q = q_tail; q < seq; ++q) {
-            const uint32_t o = s_qoff[q % kNB], z = s_qsz[q % kNB];
-            if (!(o + z <= off || off + bytes <= o)) need = q + 1u;
-        }
-        while (q_tail < need) {
+        // wait until a barrier pair and the region are free. Chunks are released in allocation order and, walking the
+        // ring forward from the head, the outstanding chunks are met oldest first: only the oldest one can be in the way.
+        const uint32_t need = seq >= (uint32_t)kNB ? seq - (uint32_t)kNB + 1u : 0u;
+        while (q_tail < seq) {
+            bool must = q_tail < need;
+            if (!must) {
+                const uint32_t o = s_qoff[q_tail % kNB], z = s_qsz[q_tail % kNB];
+                must = !(o + z <= off || off + bytes <= o);
+            }
+            if (!must) break;
             if (!mbar_wait_b(&s_empty[q_tail % kNB], (q_tail / kNB) & 1, P.abort_flag)) return false;
             ++q_tail;
         }
@@ -958,7 +992,10 @@ __device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_
         for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.up.w + (size_t)pb * 16 * KbH, 16, KbH, pitchH)) return;
         for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.down.w + (size_t)t * 16 * KbI, 16, KbI, pitchI)) return;
     }
-    for (int v = v_b0; v < v_b1; ++v) if (!issue(reinterpret_cast<const uint8_t*>(P.lm_head + (size_t)v * H), 1, 2 * H, 2 * H)) return;
+    for (int v = v_b0; v < v_b1; v += kLmRows) {  // lm_head rows are contiguous: kLmRows rows per chunk, one bulk copy
+        const int nr = min(kLmRows, v_b1 - v);
+        if (!issue(reinterpret_cast<const uint8_t*>(P.lm_head + (size_t)v * H), 1, nr * 2 * H, nr * 2 * H)) return;
+    }
 }
 
 }  // namespace
@@ -1031,8 +1068,10 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
     c.ownerC = c.nownC > 0 && tid < c.nownC * M;
     c.om = c.ownerC ? tid / c.nownC : 0;
     c.oc = c.ownerC ? tid - c.om * c.nownC : 0;
-    unsigned long long* trace = P.trace;
-    const bool tracer = cta == 0 && tid == 0;
+    const int who = cta == 0 ? 0 : (cta == ncta - 1 ? 1 : -1);
+    unsigned long long* trace = who >= 0 ? P.trace + (size_t)who * (L + 2) * kTracePoints : nullptr;
+    const bool tracer = who >= 0 && tid == 0;
+    c.trl = nullptr;
     if (tid < kMaxTok) {
         long long id = tid < M ? ids_in[tid] : 0;
         id = id < 0 ? 0 : (id >= P.V ? P.V - 1 : id);
@@ -1080,6 +1119,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         const LayerDev& Ly = P.layers[l];
         const size_t lbase = (size_t)l * P.per_layer;
         unsigned long long* tr = trace + (size_t)(1 + l) * kTracePoints;
+        c.trl = who >= 0 ? tr : nullptr;
         if (tracer) tr[0] = gtime();
         stage_qkv(c, P, l, a_b0, a_b1, s_pos);
         if (tracer) tr[1] = gtime();
@@ -1088,7 +1128,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         {   // stage C: o_proj (:580) + residual + post_attention_layernorm -> digits of gate / up inputs
             if (tid < kMaxTok) c.S.invs[tid] = pow2d(Ly.e_o - 29);
             float rr[kMaxTok];
-            residual_stage(c, P, &Ly.o, H, row_pitch(H >> 3), c.X + lbase + P.o_xC, lbase + P.o_cst, &resid, rr);
+            residual_stage(c, P, &Ly.o, H, row_pitch(H >> 3), c.X + lbase + P.o_xC, lbase + P.o_cst, &resid, rr, 8);
             if (c.ownerC) {
                 const int col = c.colC0 + c.oc;
                 const float xh = resid * rr[c.om] * ldp(Ly.ln_post, col, c.pdt);
@@ -1103,7 +1143,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         if (tracer) tr[4] = gtime();
         {   // stage D2: down_proj (:257) + residual (:918) + the next layer's input_layernorm (or the final norm, :1315)
             float rr[kMaxTok];
-            residual_stage(c, P, &Ly.down, I, row_pitch(I >> 3), c.X + lbase + P.o_xD2, lbase + P.o_d2st, &resid, rr);
+            residual_stage(c, P, &Ly.down, I, row_pitch(I >> 3), c.X + lbase + P.o_xD2, lbase + P.o_d2st, &resid, rr, 14);
             if (l + 1 < L) {
                 publish_qkv_inputs(c, P, l + 1, P.layers[l + 1].ln_in, resid, rr);
             } else {  // final RMSNorm -> fp16 x for lm_head, published as half2 words
@@ -1317,7 +1357,7 @@ int persist_create(PersistState** out, const onebit_decoder_config& cfg, const o
             fill_words_kernel<<<64, 256>>>(base + P.o_xD2, B * I, kSentD);
         }
     }
-    S->trace_words = kTracePoints * (L + 2);
+    S->trace_words = kTracers * kTracePoints * (L + 2);
     if (cudaMalloc(&S->dlayers, sizeof(LayerDev) * L) != cudaSuccess || cudaMalloc(&S->dp, sizeof(Params)) != cudaSuccess ||
         cudaMalloc(&S->step_counter, 8) != cudaSuccess || cudaMalloc(&S->abort_flag, 4) != cudaSuccess ||
         cudaMalloc(&S->trace, sizeof(unsigned long long) * S->trace_words) != cudaSuccess) {

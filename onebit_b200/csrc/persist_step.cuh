@@ -36,7 +36,8 @@ constexpr int kHeadDim = 128;
 constexpr int kRedBytes = 4 * kMaxTiles * 16 * 8 * 4;  // K-split partial sums [KG<=4 | 8][tiles][16][8] int32
 constexpr uint32_t kSentD = 0x80808080u;  // digit words: a byte 0x80 (= -128) is never a valid base-255 digit
 constexpr uint32_t kSentF = 0xFFFFFFFFu;  // float words: this NaN pattern is never produced (canonicalised away)
-constexpr int kTracePoints = 16;
+constexpr int kTracePoints = 32;  // per trace row (one row per layer, + step start, + lm_head)
+constexpr int kTracers = 2;       // CTA 0 and the last CTA record
 
 struct BLDev {
     const uint8_t* w;   // [N][K/8] packed signs
@@ -74,7 +75,7 @@ struct Params {
     size_t o_xfin, o_amax, total_words;
     unsigned long long* step_counter;
     int* abort_flag;
-    unsigned long long* trace;  // [kTracePoints * (L + 1)] globaltimer stamps of CTA 0 (always on: one store per stage)
+    unsigned long long* trace;  // [kTracers][L + 2][kTracePoints] globaltimer stamps (always on: a few stores per stage)
     long long* ids;
     int* pos;
 };
