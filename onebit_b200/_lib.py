@@ -91,6 +91,24 @@ def load() -> ctypes.CDLL:
     return _lib
 
 
+_torch_ops = None
+
+
+def torch_ops():
+    """`torch.ops.onebit_b200` (bitlinear, bitlinear_nolayernorm, pack_signs, unpack_signs): the dispatcher face of the
+    same C ABI (csrc_torch/torch_ops.cpp). Raises RuntimeError if the shim has not been built."""
+    global _torch_ops
+    if _torch_ops is None:
+        import torch
+        load()
+        path = LIB_PATH.with_name("libonebit_b200_torch.so")
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing: build it with `python -m onebit_b200.build`")
+        torch.ops.load_library(str(path))
+        _torch_ops = torch.ops.onebit_b200
+    return _torch_ops
+
+
 def last_error() -> str:
     return load().onebit_last_error().decode()
 

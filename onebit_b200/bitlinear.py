@@ -102,6 +102,10 @@ def bitlinear_forward(x: torch.Tensor, weight: torch.Tensor, weight_scale: torch
                       bias: Optional[torch.Tensor] = None, eps: float = 1e-5, variant: str = "auto") -> torch.Tensor:
     """Functional form of BitLinearInf.forward (bitnet.py:112-122) on the CUDA path. Returns a fresh tensor with
     the dtype/device of `x`."""
+    if variant == "auto":
+        # the torch dispatcher op over the same C ABI (csrc_torch/torch_ops.cpp): argument checks, output and scratch
+        # allocation and the launch happen in C++ — no ctypes marshalling on the module's forward path
+        return _lib.torch_ops().bitlinear(x, weight, weight_scale, input_factor, bias, float(eps))
     n, k = _check_layer_args(x, weight, weight_scale, input_factor, bias)
     lib = _lib.load()
     x2 = x.reshape(-1, k)

@@ -75,6 +75,32 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+TORCH_LIB = PKG / "libonebit_b200_torch.so"
+TORCH_SRC = PKG / "csrc_torch" / "torch_ops.cpp"
+
+
+def build_torch_ops(force: bool = False) -> Path:
+    """The torch dispatcher shim (TORCH_LIBRARY onebit_b200: bitlinear, bitlinear_nolayernorm, pack_signs,
+    unpack_signs) over the C ABI. Host C++ only (g++ against the installed torch headers); links libonebit_b200.so."""
+    build(force=False)
+    deps = [TORCH_SRC, PKG.parent / "include" / "onebit_b200.h"]
+    if not force and TORCH_LIB.exists() and all(d.stat().st_mtime <= TORCH_LIB.stat().st_mtime for d in deps):
+        return TORCH_LIB
+    import torch
+    tdir = Path(torch.__file__).resolve().parent
+    abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={abi}",
+           f"-I{tdir / 'include'}", f"-I{tdir / 'include' / 'torch' / 'csrc' / 'api' / 'include'}",
+           "-I/usr/local/cuda/include", f"-I{PKG.parent / 'include'}", str(TORCH_SRC), "-o", str(TORCH_LIB),
+           f"-L{tdir / 'lib'}", "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-ltorch_cuda",
+           f"-L{PKG}", f"-l:{LIB.name}", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tdir / 'lib'}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for {TORCH_SRC.name}:\n{r.stdout}\n{r.stderr}")
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(p)
+    print(build_torch_ops(force="--force" in sys.argv))

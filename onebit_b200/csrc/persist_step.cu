@@ -100,6 +100,30 @@ __device__ __noinline__ float ldp(const void* p, int i, int pdt) {  // parameter
     return static_cast<const float*>(p)[i];
 }
 
+// ---- per-layer parameter block (shared memory, filled by the TMA producer; offsets in ELEMENTS of the param dtype) ----
+constexpr int kPBScalarBytes = 64;  // 2 x 8 words: quantiser exponents of layer l and of layer l + 1 (see lscal)
+constexpr int PB_gA = 0;      // weight_scale of this CTA's q/k/v tiles, 16 per tile (<= 12 tiles)
+constexpr int PB_gO = 192;    // o_proj.weight_scale      [colC0, colC0 + nownC)
+constexpr int PB_gDn = 288;   // down_proj.weight_scale   [colC0, ...)
+constexpr int PB_lnN = 384;   // next layer's input_layernorm.weight (or the final norm) [colC0, ...)
+constexpr int PB_hq = 480, PB_hk = 576, PB_hv = 672;  // next layer's q/k/v input_factor [colC0, ...)
+constexpr int PB_lnP = 768;   // post_attention_layernorm.weight [colC0, ...)
+constexpr int PB_hg = 864, PB_hu = 960;               // gate/up input_factor [colC0, ...)
+constexpr int PB_gG = 1056, PB_gU = 1152;             // gate/up weight_scale [colD0, colD0 + nownD)
+constexpr int PB_hD = 1248;   // down_proj.input_factor [colD0, ...)
+constexpr int PB_hO = 1344;   // o_proj.input_factor of this CTA's attention head (128)
+constexpr int kPBEls = 1472;
+constexpr int kPBBytes = kPBScalarBytes + kPBEls * 4;
+__device__ __forceinline__ float pbf(const unsigned char* pb, int off_el, int i, int pdt) {
+    const unsigned char* p = pb + kPBScalarBytes;
+    if (pdt == ONEBIT_F16) return __half2float(reinterpret_cast<const __half*>(p)[off_el + i]);
+    if (pdt == ONEBIT_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[off_el + i]);
+    return reinterpret_cast<const float*>(p)[off_el + i];
+}
+// scalars of the block: word w of layer l (which = 0) or l + 1 (which = 1): 0..2 e_q/e_k/e_v, 3 e_o, 4..5 e_gate/e_up,
+// 6 max|down.input_factor| (float bits)
+__device__ __forceinline__ int pbi(const unsigned char* pb, int which, int w) { return reinterpret_cast<const int*>(pb)[which * 8 + w]; }
+
 // balanced base-255 digits of v (|v| <= 2^29): four bytes in [-127, 127], sum_d digit_d * 255^d == v
 __device__ __forceinline__ uint32_t digits255(int v) {
     const uint32_t u = (uint32_t)v + 2114125312u;  // + 127 * (1 + 255 + 255^2 + 255^3)
@@ -165,15 +189,16 @@ __device__ __forceinline__ void block_range(int nblocks, int cta, int ncta, int&
     b0 = (int)(((long long)nblocks * cta) / ncta);
     b1 = (int)(((long long)nblocks * (cta + 1)) / ncta);
 }
-__device__ __host__ __forceinline__ int row_pitch(int kb) {  // bytes per weight row in the ring: = 32 (mod 128) -> conflict-free LDS.64
-    const int r = kb & 127;
-    return kb + ((32 - r + 128) & 127);
-}
+// Weight tiles live in HBM re-tiled at load time (retile_kernel, 1 bit per element as in the checkpoint): a 16-row tile
+// is one contiguous block of 16 * K/8 bytes = [K/256 units][32 lanes][16 B], the 16 B of lane (g, t4) being the
+// 8 bytes of row g and the 8 bytes of row g + 8 that form its four A-fragment words of that unit. One bulk copy per tile,
+// one conflict-free LDS.128 per lane and unit. `pitch` below is tile_bytes / 16 = K / 8.
+__device__ __host__ __forceinline__ int row_pitch(int kb) { return kb; }
 
 struct TileInfo {
     uint32_t soff;     // byte offset of the tile inside the ring
     int pslot;         // which digit set / scale the tile's rows use
-    const void* g;     // weight_scale of the tile's first row
+    int goff;          // element offset (parameter block) of the weight_scale of the tile's first row
     int red_off;       // where the tile's K-group partial sums live in `red` (ints): [kgn][16][8]
     int kgn;           // K groups of the pass the tile belongs to
 };
@@ -188,6 +213,7 @@ __device__ __forceinline__ int pass_size(int T, int tile_bytes, int ring_bytes) 
 struct Smem {
     unsigned char* ring;
     uint32_t* dbuf;
+    unsigned char* pbuf;          // [2][kPBBytes] parameter blocks (layer parity)
     int* red;
     float* u;                     // [kMaxTok][192]
     uint32_t* stat;               // [M * ncta * kStatW] (>= 3 * ncta * 4)
@@ -211,6 +237,7 @@ struct Ctx {
     uint32_t* Xc;  // the other parity set: re-armed (sentinels) word for word as we publish
     Ring R;
     unsigned long long* trl;  // trace row of the current layer (tracer CTAs only, else nullptr)
+    const unsigned char* pb;  // parameter block of the current layer
 };
 __device__ __forceinline__ void stamp(const Ctx& c, int slot) {
     if (c.trl != nullptr && c.tid == 0) c.trl[slot] = gtime();
@@ -293,34 +320,57 @@ __device__ __forceinline__ void imma_phase(const unsigned char* ring, const Tile
 #pragma unroll
     for (int ti = 0; ti < 3; ++ti) {
         const int tt = min(t0 + ti, p0 + n - 1);
-        soff[ti] = s_tile[tt].soff + (uint32_t)(g * pitch + 8 * t4);
+        soff[ti] = s_tile[tt].soff + (uint32_t)(lane * 16);
         psl[ti] = s_tile[tt].pslot;
     }
-    for (int u = kg; u < units; u += KG) {
-        uint4 bv[4];
-        int loaded = -1;
+    (void)pitch;
+    const bool uniform = psl[0] == psl[1] && psl[1] == psl[2];
+    if (uniform) {  // the common case: one digit set for all of this warp's tiles -> tiles interleaved per plane (ILP)
+        const uint32_t* bp0 = dbuf + (size_t)psl[0] * set_words + (size_t)bm * K + bd * 16 + t4 * 4;
+        for (int u = kg; u < units; u += KG) {
+            uint4 bv[4], w[3];
 #pragma unroll
-        for (int ti = 0; ti < 3; ++ti) {
-            if (ti < nt) {
-                if (psl[ti] != loaded) {
-                    loaded = psl[ti];
-                    const uint32_t* bp = dbuf + (size_t)loaded * set_words + (size_t)bm * K + u * 256 + bd * 16 + t4 * 4;
+            for (int jp = 0; jp < 4; ++jp)
+                bv[jp] = bm < M ? *reinterpret_cast<const uint4*>(bp0 + u * 256 + jp * 64) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int ti = 0; ti < 3; ++ti)
+                w[ti] = ti < nt ? *reinterpret_cast<const uint4*>(ring + soff[ti] + u * 512) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const uint32_t mask = 0x01010101u << (2 * jp + jj);
+                    const uint32_t b0 = jj ? bv[jp].z : bv[jp].x, b1 = jj ? bv[jp].w : bv[jp].y;
+#pragma unroll
+                    for (int ti = 0; ti < 3; ++ti)
+                        if (ti < nt)
+                            imma16832(acc[ti][jj], plane(w[ti].x, mask), plane(w[ti].z, mask), plane(w[ti].y, mask), plane(w[ti].w, mask), b0, b1);
+                }
+        }
+    } else {
+        for (int u = kg; u < units; u += KG) {
+            uint4 bv[4];
+            int loaded = -1;
+#pragma unroll
+            for (int ti = 0; ti < 3; ++ti) {
+                if (ti < nt) {
+                    if (psl[ti] != loaded) {
+                        loaded = psl[ti];
+                        const uint32_t* bp = dbuf + (size_t)loaded * set_words + (size_t)bm * K + u * 256 + bd * 16 + t4 * 4;
+#pragma unroll
+                        for (int jp = 0; jp < 4; ++jp)
+                            bv[jp] = bm < M ? *reinterpret_cast<const uint4*>(bp + jp * 64) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    const uint4 w = *reinterpret_cast<const uint4*>(ring + soff[ti] + u * 512);
 #pragma unroll
                     for (int jp = 0; jp < 4; ++jp)
-                        bv[jp] = bm < M ? *reinterpret_cast<const uint4*>(bp + jp * 64) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const uint32_t mask = 0x01010101u << (2 * jp + jj);
+                            imma16832(acc[ti][jj], plane(w.x, mask), plane(w.z, mask), plane(w.y, mask), plane(w.w, mask),
+                                      jj ? bv[jp].z : bv[jp].x, jj ? bv[jp].w : bv[jp].y);
+                        }
                 }
-                const unsigned char* wp = ring + soff[ti] + u * 32;
-                const uint2 w0 = *reinterpret_cast<const uint2*>(wp);
-                const uint2 w1 = *reinterpret_cast<const uint2*>(wp + 8 * pitch);
-#pragma unroll
-                for (int jp = 0; jp < 4; ++jp)
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        const uint32_t mask = 0x01010101u << (2 * jp + jj);
-                        const uint32_t a0 = plane(w0.x, mask), a1 = plane(w1.x, mask);
-                        const uint32_t a2 = plane(w0.y, mask), a3 = plane(w1.y, mask);
-                        imma16832(acc[ti][jj], a0, a1, a2, a3, jj ? bv[jp].z : bv[jp].x, jj ? bv[jp].w : bv[jp].y);
-                    }
             }
         }
     }
@@ -346,11 +396,11 @@ __device__ __noinline__ float row_value(const int* red, const TileInfo* ti, int 
 }
 
 // describe tile i of a T-tile stage (executed by thread i while every thread walks the ring allocator)
-__device__ __noinline__ void put_tile(Ctx& c, int i, int T, int pitch, uint32_t off, int pslot, const void* gbase, int row0) {
+__device__ __noinline__ void put_tile(Ctx& c, int i, int T, int pitch, uint32_t off, int pslot, int goff) {
     TileInfo& t = c.S.tile[i];
     t.soff = off;
     t.pslot = pslot;
-    t.g = static_cast<const char*>(gbase) + (size_t)row0 * dsize(c.pdt);
+    t.goff = goff;
     const int ps = pass_size(T, 16 * pitch, c.ring_bytes);
     const int p = i / ps, n = min(ps, T - p * ps);
     t.kgn = kCW / tg_of(n);
@@ -377,6 +427,7 @@ __device__ __noinline__ void stage_core(Ctx& c, int K, int pitch, int T, uint32_
             mbar_wait_b(&c.full[sq % kNB], (sq / kNB) & 1, c.abort_flag);
         }
         cta_sync();
+        if (p0 == 0) stamp(c, ts == 6 ? 20 : (ts == 8 ? 21 : (ts == 11 ? 22 : 23)));  // weights of the first pass are in
         imma_phase(c.S.ring, c.S.tile, p0, n, K, pitch, c.S.dbuf, set_words, c.M, c.S.red, c.warp, c.lane);
         cta_sync();
         if (c.tid < n) mbar_arrive(&c.empty[(seq0 + (uint32_t)(p0 + c.tid)) % kNB]);
@@ -449,14 +500,28 @@ __device__ __noinline__ void stats_exchange(Ctx& c, size_t soff, int nq, int nma
 }
 
 // x_hat = resid * rr[token] * ln_w -> x' for q, k, v of layer l -> digits -> exchange (inputs of stage A)   (:67-81)
-__device__ __noinline__ void publish_qkv_inputs(Ctx& c, const Params& P, int l, const void* lnw, float resid, const float* rr) {
-    const LayerDev& Ly = P.layers[l];
+// FROM_BLOCK: parameters of layer l come from the parameter block of layer l - 1 ("next layer" slices); else (layer 0,
+// once per step) straight from global memory.
+template <bool FROM_BLOCK>
+__device__ __noinline__ void publish_qkv_inputs(Ctx& c, const Params& P, int l, float resid, const float* rr) {
     if (c.ownerC) {
+        float lw, hq, hk, hv;
+        int eq, ek, ev;
+        if (FROM_BLOCK) {
+            lw = pbf(c.pb, PB_lnN, c.oc, c.pdt); hq = pbf(c.pb, PB_hq, c.oc, c.pdt);
+            hk = pbf(c.pb, PB_hk, c.oc, c.pdt); hv = pbf(c.pb, PB_hv, c.oc, c.pdt);
+            eq = pbi(c.pb, 1, 0); ek = pbi(c.pb, 1, 1); ev = pbi(c.pb, 1, 2);
+        } else {
+            const LayerDev& Ly = P.layers[l];
+            const int col = c.colC0 + c.oc;
+            lw = ldp(Ly.ln_in, col, c.pdt); hq = ldp(Ly.q.h, col, c.pdt); hk = ldp(Ly.k.h, col, c.pdt); hv = ldp(Ly.v.h, col, c.pdt);
+            eq = Ly.e_qkv[0]; ek = Ly.e_qkv[1]; ev = Ly.e_qkv[2];
+        }
         const int col = c.colC0 + c.oc;
-        const float xh = resid * rr[c.om] * ldp(lnw, col, c.pdt);
-        c.S.stage[(size_t)(c.om * 3 + 0) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.q.h, col, c.pdt), Ly.e_qkv[0], col);
-        c.S.stage[(size_t)(c.om * 3 + 1) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.k.h, col, c.pdt), Ly.e_qkv[1], col);
-        c.S.stage[(size_t)(c.om * 3 + 2) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.v.h, col, c.pdt), Ly.e_qkv[2], col);
+        const float xh = resid * rr[c.om] * lw;
+        c.S.stage[(size_t)(c.om * 3 + 0) * c.nownC + c.oc] = quant_digits(xh * hq, eq, col);
+        c.S.stage[(size_t)(c.om * 3 + 1) * c.nownC + c.oc] = quant_digits(xh * hk, ek, col);
+        c.S.stage[(size_t)(c.om * 3 + 2) * c.nownC + c.oc] = quant_digits(xh * hv, ev, col);
     }
     cta_sync();
     publish32(c, (size_t)l * P.per_layer + P.o_xA, (size_t)kMaxTok * c.H, (size_t)c.H, 3, c.nownC, c.colC0);
@@ -465,20 +530,20 @@ __device__ __noinline__ void publish_qkv_inputs(Ctx& c, const Params& P, int l, 
 // stages C / D2 share their shape: rows of o_proj / down_proj owned as 32-row blocks, then
 // x <- x + LayerNorm(g*t) (:912 / :918) and the RMSNorm factor of the next BitLinear group (:67-81), all from ONE
 // exchange of five per-CTA sums (sum u, sum u^2, sum r, sum r^2, sum r*u).
-__device__ __noinline__ void residual_stage(Ctx& c, const Params& P, const BLDev* bl, int K, int pitch, const uint32_t* xin0, size_t o_stat,
+__device__ __noinline__ void residual_stage(Ctx& c, const Params& P, int gbase_el, int K, int pitch, const uint32_t* xin0, size_t o_stat,
                                             float* resid_io, float* rr_out /*[M]*/, int ts) {
     const int T = c.nownC >> 4;
     const uint32_t seq0 = c.R.seq;
     for (int i = 0; i < T; ++i) {
         uint32_t seq;
         const uint32_t off = c.R.alloc(16u * pitch, seq);
-        if (c.tid == i) put_tile(c, i, T, pitch, off, 0, bl->g, c.colC0 + 16 * i);
+        if (c.tid == i) put_tile(c, i, T, pitch, off, 0, gbase_el + 16 * i);
     }
     stage_core(c, K, pitch, T, seq0, 1, xin0, xin0, ts);
     float u = 0.f, resid = *resid_io;
     if (c.ownerC) {
         const TileInfo* ti = &c.S.tile[c.oc >> 4];
-        u = row_value(c.S.red, ti, c.oc & 15, c.om, (long long)c.S.q128[c.om], c.S.invs[c.om]) * ldp(ti->g, c.oc & 15, c.pdt);
+        u = row_value(c.S.red, ti, c.oc & 15, c.om, (long long)c.S.q128[c.om], c.S.invs[c.om]) * pbf(c.pb, ti->goff, c.oc & 15, c.pdt);
         c.S.u[c.om * 192 + c.oc] = u;
         c.S.u[c.om * 192 + 96 + c.oc] = resid;
     }
@@ -527,7 +592,6 @@ __device__ __noinline__ void residual_stage(Ctx& c, const Params& P, const BLDev
 
 // stage A: q, k, v = BitLinear(RMSNorm(x)) (:522-524) — publishes raw g*t and per-CTA LayerNorm partials
 __device__ __noinline__ void stage_qkv(Ctx& c, const Params& P, int l, int a_b0, int a_b1, const int* s_pos) {
-    const LayerDev& Ly = P.layers[l];
     const int H = c.H, tH = H >> 4, pitchH = row_pitch(H >> 3);
     const int gt0 = 2 * a_b0, gt1 = 2 * a_b1, T = gt1 - gt0;
     const int p_lo = gt0 / tH, nsets = (gt1 - 1) / tH - p_lo + 1;
@@ -539,11 +603,11 @@ __device__ __noinline__ void stage_qkv(Ctx& c, const Params& P, int l, int a_b0,
         const uint32_t off = c.R.alloc(16u * pitchH, seq);
         if (c.tid == i) {
             const int gt = gt0 + i, prob = gt / tH, row0 = (gt - prob * tH) * 16;
-            const BLDev& b = prob == 0 ? Ly.q : (prob == 1 ? Ly.k : Ly.v);
-            put_tile(c, i, T, pitchH, off, prob - p_lo, b.g, row0);
+            (void)row0;
+            put_tile(c, i, T, pitchH, off, prob - p_lo, PB_gA + 16 * i);
         }
     }
-    if (c.tid < 2 * kMaxTok) c.S.invs[c.tid] = pow2d(Ly.e_qkv[min(p_lo + c.tid / kMaxTok, 2)] - 29);
+    if (c.tid < 2 * kMaxTok) c.S.invs[c.tid] = pow2d(pbi(c.pb, 0, min(p_lo + c.tid / kMaxTok, 2)) - 29);
     // attention CTAs: pull this layer's cached K/V rows of their (sequence, head) towards L2
     if (c.cta < P.heads * c.M) {
         const int am = c.cta / P.heads, ah = c.cta - am * P.heads;
@@ -563,7 +627,7 @@ __device__ __noinline__ void stage_qkv(Ctx& c, const Params& P, int l, int a_b0,
         if (em < c.M) {
             const TileInfo* ti = &c.S.tile[er >> 4];
             const float u = row_value(c.S.red, ti, er & 15, em, (long long)c.S.q128[ti->pslot * kMaxTok + em], c.S.invs[ti->pslot * kMaxTok + em]) *
-                            ldp(ti->g, er & 15, c.pdt);
+                            pbf(c.pb, ti->goff, er & 15, c.pdt);
             c.S.u[em * 192 + er] = u;
             stv1(XL + a, fbits(u));
         }
@@ -598,7 +662,6 @@ __device__ __noinline__ void stage_qkv(Ctx& c, const Params& P, int l, int a_b0,
 // stage B: attention for one new token per sequence (:536-563): LayerNorm of q/k/v (bitnet.py:118) from the partials,
 // RoPE (:176-181), cache append, fp32 online softmax over the cache, digits of o_proj's input
 __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, const int* s_pos) {
-    const LayerDev& Ly = P.layers[l];
     const int H = c.H, tid = c.tid, lane = c.lane, warp = c.warp, ncta = c.ncta;
     uint32_t* XL = c.X + (size_t)l * P.per_layer;
     uint32_t* XLc = c.Xc + (size_t)l * P.per_layer;
@@ -721,7 +784,7 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
             num += part[w * 132 + 4 + tid] * f;
         }
         const int col = ah * kHeadDim + tid;
-        c.S.stage[tid] = quant_digits((num / den) * ldp(Ly.o.h, col, c.pdt), Ly.e_o, col);
+        c.S.stage[tid] = quant_digits((num / den) * pbf(c.pb, PB_hO, tid, c.pdt), pbi(c.pb, 0, 3), col);
     }
     cta_sync();
     if (tid < 128) {
@@ -738,7 +801,6 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
 // stage D1: gate, up (:257) — 16 gate rows + 16 up rows of the same columns live in the same CTA, so
 // silu(LN(gate)) * LN(up) * input_factor(down) is finished by the owner after ONE exchange of sums and bounds
 __device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d_b0, int d_b1) {
-    const LayerDev& Ly = P.layers[l];
     const int H = c.H, I = c.I, pitchH = row_pitch(H >> 3), tid = c.tid, lane = c.lane, warp = c.warp;
     (void)I;
     uint32_t* XL = c.X + (size_t)l * P.per_layer;
@@ -750,10 +812,10 @@ __device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d
         const uint32_t off = c.R.alloc(16u * pitchH, seq);
         if (tid == i) {
             const bool up = i >= npb;
-            put_tile(c, i, T, pitchH, off, up ? 1 : 0, up ? Ly.up.g : Ly.gate.g, 16 * (d_b0 + (up ? i - npb : i)));
+            put_tile(c, i, T, pitchH, off, up ? 1 : 0, up ? PB_gU + 16 * (i - npb) : PB_gG + 16 * i);
         }
     }
-    if (tid < 2 * kMaxTok) c.S.invs[tid] = pow2d(Ly.e_gu[tid / kMaxTok] - 29);
+    if (tid < 2 * kMaxTok) c.S.invs[tid] = pow2d(pbi(c.pb, 0, 4 + tid / kMaxTok) - 29);
     stage_core(c, H, pitchH, T, seq0, 2, XL + P.o_xD1, XL + P.o_xD1 + (size_t)kMaxTok * H, 11);
     const int Rr = 16 * T;
     if (Rr > 0) {
@@ -761,7 +823,7 @@ __device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d
         if (em < c.M) {
             const TileInfo* ti = &c.S.tile[er >> 4];
             c.S.u[em * 192 + er] = row_value(c.S.red, ti, er & 15, em, (long long)c.S.q128[ti->pslot * kMaxTok + em], c.S.invs[ti->pslot * kMaxTok + em]) *
-                                   ldp(ti->g, er & 15, c.pdt);
+                                   pbf(c.pb, ti->goff, er & 15, c.pdt);
         }
     }
     cta_sync();
@@ -772,7 +834,7 @@ __device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d
     if (ownerD) {
         gv = c.S.u[dm * 192 + dc];
         uv = c.S.u[dm * 192 + nown + dc];
-        hd = ldp(Ly.down.h, col0 + dc, c.pdt);
+        hd = pbf(c.pb, PB_hD, dc, c.pdt);
     }
     if (warp < kMaxTok) {
         const int m = warp;
@@ -780,7 +842,7 @@ __device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d
         float mx[3] = {0.f, 0.f, 0.f};
         if (m < c.M)
             for (int k = lane; k < nown; k += 32) {
-                const float gf = c.S.u[m * 192 + k], uf = c.S.u[m * 192 + nown + k], hf = fabsf(ldp(Ly.down.h, col0 + k, c.pdt));
+                const float gf = c.S.u[m * 192 + k], uf = c.S.u[m * 192 + nown + k], hf = fabsf(pbf(c.pb, PB_hD, k, c.pdt));
                 s[0] += (double)gf; s[1] += (double)gf * (double)gf; s[2] += (double)uf; s[3] += (double)uf * (double)uf;
                 mx[0] = fmaxf(mx[0], fabsf(gf * uf) * hf); mx[1] = fmaxf(mx[1], fabsf(gf) * hf); mx[2] = fmaxf(mx[2], fabsf(uf) * hf);
             }
@@ -810,7 +872,7 @@ __device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d
         ln_finish(rd[2], rd[3], P.inv_I, P.ln_eps, &mu, &ru);
         const float amg = fabsf(mg), amu = fabsf(mu);
         // |silu(g^) u^ h| <= |g^||u^||h| <= rg ru (|g u h| + |mg||u h| + |mu||g h| + |mg mu||h|)
-        const float bound = rg * ru * ((float)rd[4] + amg * (float)rd[6] + amu * (float)rd[5] + amg * amu * Ly.hmax_down) * 1.0001f;
+        const float bound = rg * ru * ((float)rd[4] + amg * (float)rd[6] + amu * (float)rd[5] + amg * amu * __int_as_float(pbi(c.pb, 0, 6))) * 1.0001f;
         int e = 0;
         if (bound > 0.f && bound < 3.0e38f) frexpf(bound, &e);
         float* f = c.S.fscr + tid * 8;
@@ -942,59 +1004,102 @@ __device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, in
     }
 }
 
-// TMA producer warp: walks the static schedule of this CTA's weight tiles, independent of the dependency chain
-__device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_raw, int ring_bytes, uint64_t* s_full, uint64_t* s_empty,
-                                           uint32_t* s_qoff, uint32_t* s_qsz, int lane, int a_b0, int a_b1, int c_b0, int c_b1, int d_b0,
-                                           int d_b1, int v_b0, int v_b1) {
-    const int H = P.H, I = P.I, KbH = H >> 3, KbI = I >> 3, pitchH = row_pitch(KbH), pitchI = row_pitch(KbI), tH = H >> 4;
+// TMA producer warp: walks the static schedule of this CTA's weight tiles, independent of the dependency chain.
+// Per layer it first fetches the layer's PARAMETER BLOCK (every weight_scale / input_factor / norm-weight slice and
+// quantiser exponent this CTA's compute warps will touch in the layer, see PB_* above) into one of two shared-memory
+// buffers, so that no parameter load ever sits on the dependency chain.
+__device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_raw, unsigned char* pbuf, int ring_bytes, uint64_t* s_full,
+                                           uint64_t* s_empty, uint64_t* s_pfull, uint64_t* s_pempty, int lane, int cta, int M, int a_b0, int a_b1, int c_b0, int c_b1, int d_b0, int d_b1, int v_b0,
+                                           int v_b1) {
+    const int H = P.H, I = P.I, tH = H >> 4, L = P.L;
+    const uint32_t tileH = 2u * (uint32_t)H, tileI = 2u * (uint32_t)I;  // bytes of a re-tiled 16-row tile
     Ring R;
     R.head = 0; R.cap = (uint32_t)ring_bytes; R.seq = 0;
     uint32_t q_tail = 0;  // oldest unreleased chunk
+    uint32_t my_off = 0, my_sz = 0, my_q = 0xFFFFFFFFu;
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    auto issue = [&](const uint8_t* src, int rows, int row_bytes, int pitch) -> bool {
+    auto issue = [&](const uint8_t* src, uint32_t bytes) -> bool {
         uint32_t seq;
-        const uint32_t bytes = (uint32_t)(rows * pitch);
         const uint32_t off = R.alloc(bytes, seq);
-        // wait until a barrier pair and the region are free. Chunks are released in allocation order and, walking the
-        // ring forward from the head, the outstanding chunks are met oldest first: only the oldest one can be in the way.
-        const uint32_t need = seq >= (uint32_t)kNB ? seq - (uint32_t)kNB + 1u : 0u;
-        while (q_tail < seq) {
-            bool must = q_tail < need;
-            if (!must) {
-                const uint32_t o = s_qoff[q_tail % kNB], z = s_qsz[q_tail % kNB];
-                must = !(o + z <= off || off + bytes <= o);
-            }
-            if (!must) break;
+        // wait until a barrier pair and the region are free: every outstanding chunk that overlaps the new region must
+        // have been released, and chunks are released in allocation order. Lane i remembers the chunk in barrier slot i.
+        uint32_t need = seq >= (uint32_t)kNB ? seq - (uint32_t)kNB + 1u : 0u;
+        const bool ov = my_q != 0xFFFFFFFFu && my_q >= q_tail && my_q < seq && !(my_off + my_sz <= off || off + bytes <= my_off);
+        need = max(need, __reduce_max_sync(0xffffffffu, ov ? my_q + 1u : 0u));
+        while (q_tail < need) {
             if (!mbar_wait_b(&s_empty[q_tail % kNB], (q_tail / kNB) & 1, P.abort_flag)) return false;
             ++q_tail;
         }
-        __syncwarp();
+        if (lane == (int)(seq % kNB)) { my_off = off; my_sz = bytes; my_q = seq; }
         if (lane == 0) {
-            s_qoff[seq % kNB] = off;
-            s_qsz[seq % kNB] = bytes;
-            mbar_expect_tx(&s_full[seq % kNB], (uint32_t)(rows * row_bytes));
+            mbar_expect_tx(&s_full[seq % kNB], bytes);
+            bulk_g2s_hint(smem_raw + off, src, bytes, &s_full[seq % kNB], pol);
         }
         __syncwarp();
-        for (int r = lane; r < rows; r += 32)
-            bulk_g2s_hint(smem_raw + off + (size_t)r * pitch, src + (size_t)r * row_bytes, (uint32_t)row_bytes, &s_full[seq % kNB], pol);
         return true;
     };
-    for (int l = 0; l < P.L; ++l) {
+    const int es = (int)dsize(P.pdt);
+    const int nownC = 32 * (c_b1 - c_b0), colC0 = 32 * c_b0, nownD = 16 * (d_b1 - d_b0), colD0 = 16 * d_b0, TA = 2 * (a_b1 - a_b0);
+    const bool attn = cta < P.heads * M;
+    for (int l = 0; l < L; ++l) {
         const LayerDev& Ly = P.layers[l];
-        for (int gt = 2 * a_b0; gt < 2 * a_b1; ++gt) {
-            const int prob = gt / tH, row0 = (gt - prob * tH) * 16;
-            const uint8_t* w = prob == 0 ? Ly.q.w : (prob == 1 ? Ly.k.w : Ly.v.w);
-            if (!issue(w + (size_t)row0 * KbH, 16, KbH, pitchH)) return;
+        {   // ---- parameter block of layer l: lane i owns copy i
+            unsigned char* pb = pbuf + (size_t)(l & 1) * kPBBytes;
+            if (!mbar_wait_b(&s_pempty[l & 1], ((l >> 1) & 1) ^ 1, P.abort_flag)) return;
+            const bool last = l + 1 == L;
+            const LayerDev& Ln = P.layers[last ? l : l + 1];
+            const char* src = nullptr;
+            uint32_t bytes = 0, dst = 0;
+            auto slice = [&](const void* base, int first, int count, int off_el) {
+                src = static_cast<const char*>(base) + (size_t)first * es;
+                bytes = (uint32_t)(count * es);
+                dst = (uint32_t)(kPBScalarBytes + off_el * es);
+            };
+            switch (lane) {
+                case 0: src = reinterpret_cast<const char*>(P.lscal + (size_t)l * 8); bytes = kPBScalarBytes; dst = 0; break;
+                case 1: slice(Ly.o.g, colC0, nownC, PB_gO); break;
+                case 2: slice(Ly.down.g, colC0, nownC, PB_gDn); break;
+                case 3: slice(last ? P.final_norm : Ln.ln_in, colC0, nownC, PB_lnN); break;
+                case 4: if (!last) slice(Ln.q.h, colC0, nownC, PB_hq); break;
+                case 5: if (!last) slice(Ln.k.h, colC0, nownC, PB_hk); break;
+                case 6: if (!last) slice(Ln.v.h, colC0, nownC, PB_hv); break;
+                case 7: slice(Ly.ln_post, colC0, nownC, PB_lnP); break;
+                case 8: slice(Ly.gate.h, colC0, nownC, PB_hg); break;
+                case 9: slice(Ly.up.h, colC0, nownC, PB_hu); break;
+                case 10: slice(Ly.gate.g, colD0, nownD, PB_gG); break;
+                case 11: slice(Ly.up.g, colD0, nownD, PB_gU); break;
+                case 12: slice(Ly.down.h, colD0, nownD, PB_hD); break;
+                case 13: if (attn) slice(Ly.o.h, (cta % P.heads) * kHeadDim, kHeadDim, PB_hO); break;
+                default: {
+                    const int i = lane - 14;
+                    if (i < TA) {
+                        const int gt = 2 * a_b0 + i, prob = gt / tH, row0 = (gt - prob * tH) * 16;
+                        slice(prob == 0 ? Ly.q.g : (prob == 1 ? Ly.k.g : Ly.v.g), row0, 16, PB_gA + 16 * i);
+                    }
+                }
+            }
+            uint32_t total = bytes;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            if (lane == 0) mbar_expect_tx(&s_pfull[l & 1], total);
+            __syncwarp();
+            if (bytes) imma::bulk_g2s(pb + dst, src, bytes, &s_pfull[l & 1]);
+            __syncwarp();
         }
-        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.o.w + (size_t)t * 16 * KbH, 16, KbH, pitchH)) return;
-        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.gate.w + (size_t)pb * 16 * KbH, 16, KbH, pitchH)) return;
-        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.up.w + (size_t)pb * 16 * KbH, 16, KbH, pitchH)) return;
-        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.down.w + (size_t)t * 16 * KbI, 16, KbI, pitchI)) return;
+        for (int gt = 2 * a_b0; gt < 2 * a_b1; ++gt) {
+            const int prob = gt / tH, lt = gt - prob * tH;
+            const uint8_t* w = prob == 0 ? Ly.q.w : (prob == 1 ? Ly.k.w : Ly.v.w);
+            if (!issue(w + (size_t)lt * tileH, tileH)) return;
+        }
+        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.o.w + (size_t)t * tileH, tileH)) return;
+        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.gate.w + (size_t)pb * tileH, tileH)) return;
+        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.up.w + (size_t)pb * tileH, tileH)) return;
+        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.down.w + (size_t)t * tileI, tileI)) return;
     }
     for (int v = v_b0; v < v_b1; v += kLmRows) {  // lm_head rows are contiguous: kLmRows rows per chunk, one bulk copy
         const int nr = min(kLmRows, v_b1 - v);
-        if (!issue(reinterpret_cast<const uint8_t*>(P.lm_head + (size_t)v * H), 1, nr * 2 * H, nr * 2 * H)) return;
+        if (!issue(reinterpret_cast<const uint8_t*>(P.lm_head + (size_t)v * H), (uint32_t)(nr * 2 * H))) return;
     }
 }
 
@@ -1007,9 +1112,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in, float* __restrict__ logits, int M,
             int ring_bytes, int dbuf_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[kNB], s_empty[kNB];
+    __shared__ __align__(8) uint64_t s_full[kNB], s_empty[kNB], s_pfull[2], s_pempty[2];
     __shared__ Params P;
-    __shared__ uint32_t s_qoff[kNB], s_qsz[kNB];
     __shared__ int s_tok[kMaxTok], s_pos[kMaxTok];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1025,6 +1129,10 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 1);
         }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_pfull[i], 1);
+            mbar_init(&s_pempty[i], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1036,7 +1144,8 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
     block_range(P.V, cta, ncta, v_b0, v_b1);          // lm_head rows
 
     if (warp == kCW) {
-        producer_loop(P, smem_raw, ring_bytes, s_full, s_empty, s_qoff, s_qsz, lane, a_b0, a_b1, c_b0, c_b1, d_b0, d_b1, v_b0, v_b1);
+        producer_loop(P, smem_raw, smem_raw + ring_bytes + dbuf_bytes, ring_bytes, s_full, s_empty, s_pfull, s_pempty, lane, cta,
+                      M, a_b0, a_b1, c_b0, c_b1, d_b0, d_b1, v_b0, v_b1);
         return;
     }
 
@@ -1048,6 +1157,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         unsigned char* p = smem_raw;
         c.S.ring = p; p += ring_bytes;
         c.S.dbuf = reinterpret_cast<uint32_t*>(p); p += dbuf_bytes;
+        c.S.pbuf = p; p += 2 * kPBBytes;
         c.S.red = reinterpret_cast<int*>(p); p += kRedBytes;
         c.S.stat = reinterpret_cast<uint32_t*>(p); p += (size_t)M * ncta * kStatW * 4;
         c.S.u = reinterpret_cast<float*>(p); p += kMaxTok * 192 * 4;
@@ -1112,28 +1222,31 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
             cta_sync();
             if (c.ownerC && c.om == m) resid = __half2float(erow[c.colC0 + c.oc]);
         }
-        publish_qkv_inputs(c, P, 0, P.layers[0].ln_in, resid, rr);
+        publish_qkv_inputs<false>(c, P, 0, resid, rr);
     }
 
     for (int l = 0; l < L; ++l) {
-        const LayerDev& Ly = P.layers[l];
         const size_t lbase = (size_t)l * P.per_layer;
         unsigned long long* tr = trace + (size_t)(1 + l) * kTracePoints;
         c.trl = who >= 0 ? tr : nullptr;
+        c.pb = c.S.pbuf + (size_t)(l & 1) * kPBBytes;
         if (tracer) tr[0] = gtime();
+        // the layer's parameter block has long arrived (the producer runs a layer ahead); the first readers are the
+        // threads that set the stage scales, everybody else reads it after a CTA barrier
+        if (tid < 2 * kMaxTok) mbar_wait_b(&s_pfull[l & 1], (l >> 1) & 1, c.abort_flag);
         stage_qkv(c, P, l, a_b0, a_b1, s_pos);
         if (tracer) tr[1] = gtime();
         stage_attention(c, P, l, s_pos);
         if (tracer) tr[2] = gtime();
         {   // stage C: o_proj (:580) + residual + post_attention_layernorm -> digits of gate / up inputs
-            if (tid < kMaxTok) c.S.invs[tid] = pow2d(Ly.e_o - 29);
+            if (tid < kMaxTok) c.S.invs[tid] = pow2d(pbi(c.pb, 0, 3) - 29);
             float rr[kMaxTok];
-            residual_stage(c, P, &Ly.o, H, row_pitch(H >> 3), c.X + lbase + P.o_xC, lbase + P.o_cst, &resid, rr, 8);
+            residual_stage(c, P, PB_gO, H, row_pitch(H >> 3), c.X + lbase + P.o_xC, lbase + P.o_cst, &resid, rr, 8);
             if (c.ownerC) {
                 const int col = c.colC0 + c.oc;
-                const float xh = resid * rr[c.om] * ldp(Ly.ln_post, col, c.pdt);
-                c.S.stage[(size_t)(c.om * 2 + 0) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.gate.h, col, c.pdt), Ly.e_gu[0], col);
-                c.S.stage[(size_t)(c.om * 2 + 1) * c.nownC + c.oc] = quant_digits(xh * ldp(Ly.up.h, col, c.pdt), Ly.e_gu[1], col);
+                const float xh = resid * rr[c.om] * pbf(c.pb, PB_lnP, c.oc, c.pdt);
+                c.S.stage[(size_t)(c.om * 2 + 0) * c.nownC + c.oc] = quant_digits(xh * pbf(c.pb, PB_hg, c.oc, c.pdt), pbi(c.pb, 0, 4), col);
+                c.S.stage[(size_t)(c.om * 2 + 1) * c.nownC + c.oc] = quant_digits(xh * pbf(c.pb, PB_hu, c.oc, c.pdt), pbi(c.pb, 0, 5), col);
             }
             cta_sync();
             publish32(c, lbase + P.o_xD1, (size_t)kMaxTok * H, (size_t)H, 2, c.nownC, c.colC0);
@@ -1143,12 +1256,12 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         if (tracer) tr[4] = gtime();
         {   // stage D2: down_proj (:257) + residual (:918) + the next layer's input_layernorm (or the final norm, :1315)
             float rr[kMaxTok];
-            residual_stage(c, P, &Ly.down, I, row_pitch(I >> 3), c.X + lbase + P.o_xD2, lbase + P.o_d2st, &resid, rr, 14);
+            residual_stage(c, P, PB_gDn, I, row_pitch(I >> 3), c.X + lbase + P.o_xD2, lbase + P.o_d2st, &resid, rr, 14);
             if (l + 1 < L) {
-                publish_qkv_inputs(c, P, l + 1, P.layers[l + 1].ln_in, resid, rr);
+                publish_qkv_inputs<true>(c, P, l + 1, resid, rr);
             } else {  // final RMSNorm -> fp16 x for lm_head, published as half2 words
                 float* xf = reinterpret_cast<float*>(c.S.stage);
-                if (c.ownerC) xf[c.om * 96 + c.oc] = resid * rr[c.om] * ldp(P.final_norm, c.colC0 + c.oc, c.pdt);
+                if (c.ownerC) xf[c.om * 96 + c.oc] = resid * rr[c.om] * pbf(c.pb, PB_lnN, c.oc, c.pdt);
                 cta_sync();
                 const int pairs = c.nownC / 2;
                 uint32_t* Xt = c.X + (size_t)L * P.per_layer;
@@ -1165,6 +1278,8 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
                 }
             }
         }
+        // every read of this layer's parameter block lies before the CTA barrier inside the publish above
+        if (tid == 0) mbar_arrive(&s_pempty[l & 1]);
         if (tracer) tr[5] = gtime();
     }
     unsigned long long* tr = trace + (size_t)(1 + L) * kTracePoints;
@@ -1181,6 +1296,8 @@ struct PersistState {
     persist::Params hp;              // host copy
     persist::Params* dp = nullptr;   // device copy
     persist::LayerDev* dlayers = nullptr;
+    int* lscal = nullptr;
+    uint8_t* wtiled = nullptr;       // all packed sign matrices, re-tiled (see row_pitch)
     uint32_t* xch[2] = {nullptr, nullptr};
     unsigned long long* step_counter = nullptr;
     int* abort_flag = nullptr;
@@ -1193,6 +1310,18 @@ struct PersistState {
 namespace {
 
 using namespace persist;
+
+// [N][K/8] checkpoint layout -> tile-major fragment order (see row_pitch): one thread per 8 bytes of output
+__global__ void retile_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int N, int Kb) {
+    const size_t total = (size_t)N * Kb / 8;
+    const int U = Kb / 32;
+    for (size_t o8 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o8 < total; o8 += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = o8 / ((size_t)U * 64);
+        const int r = (int)(o8 - t * (size_t)U * 64), u = r >> 6, q = r & 63, lane = q >> 1, half = q & 1, g = lane >> 2, t4 = lane & 3;
+        const size_t row = t * 16 + g + 8 * half;
+        reinterpret_cast<uint2*>(out)[o8] = *reinterpret_cast<const uint2*>(in + row * Kb + u * 32 + 8 * t4);
+    }
+}
 
 __global__ void fill_words_kernel(uint32_t* p, size_t n, uint32_t v) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -1225,7 +1354,7 @@ size_t round4(size_t w) { return (w + 3) & ~(size_t)3; }
 void plan_smem(const Params& P, int M, int smem_limit, Geometry* g) {
     const int dbuf = (int)std::max<size_t>((size_t)2 * M * P.H * 4, (size_t)M * P.I * 4);
     const int fixed = kRedBytes + M * P.ncta * kStatW * 4 + kMaxTok * 192 * 4 + kMaxTok * 96 * 3 * 4 + 32 * 8 + 2 * kMaxTok * 8 * 2 +
-                      kMaxTiles * (int)sizeof(TileInfo) + 64 * 4 + 128;
+                      kMaxTiles * (int)sizeof(TileInfo) + 64 * 4 + 128 + 2 * kPBBytes;
     g->dbuf_bytes = (dbuf + 127) & ~127;
     g->ring_bytes = ((smem_limit - 2048 - fixed - g->dbuf_bytes) / 128) * 128;
     g->smem_bytes = g->ring_bytes + g->dbuf_bytes + fixed;
@@ -1324,6 +1453,35 @@ int persist_create(PersistState** out, const onebit_decoder_config& cfg, const o
             for (int k = 0; k < I; ++k) mx = std::max(mx, std::fabs((double)h[k]));
             d.hmax_down = (float)mx;
         }
+    }
+    // ---- re-tiled copies of the packed sign matrices (1 bit per element, MMA-fragment order inside 16-row tiles)
+    {
+        const size_t per_layer_bytes = ((size_t)4 * H * H + (size_t)3 * H * I) / 8;
+        cudaError_t e = cudaMalloc(&S->wtiled, per_layer_bytes * L);
+        if (e != cudaSuccess) { persist_destroy(S); return fail(ONEBIT_ERR_CUDA, std::string("persist_create: cudaMalloc(weights): ") + cudaGetErrorString(e)); }
+        uint8_t* wp = S->wtiled;
+        for (int l = 0; l < L; ++l) {
+            BLDev* bl[7] = {&hl[l].q, &hl[l].k, &hl[l].v, &hl[l].o, &hl[l].gate, &hl[l].up, &hl[l].down};
+            const int Ns[7] = {H, H, H, H, I, I, H}, Ks[7] = {H, H, H, H, H, H, I};
+            for (int i = 0; i < 7; ++i) {
+                retile_kernel<<<592, 256>>>(bl[i]->w, wp, Ns[i], Ks[i] / 8);
+                bl[i]->w = wp;
+                wp += (size_t)Ns[i] * Ks[i] / 8;
+            }
+        }
+        ONEBIT_CUDA_TRY(cudaGetLastError());
+    }
+    {
+        std::vector<int> sc((size_t)(L + 1) * 8, 0);
+        for (int l = 0; l < L; ++l) {
+            int* w = &sc[(size_t)l * 8];
+            w[0] = hl[l].e_qkv[0]; w[1] = hl[l].e_qkv[1]; w[2] = hl[l].e_qkv[2]; w[3] = hl[l].e_o;
+            w[4] = hl[l].e_gu[0]; w[5] = hl[l].e_gu[1];
+            memcpy(&w[6], &hl[l].hmax_down, 4);
+        }
+        if (cudaMalloc(&S->lscal, sc.size() * 4) != cudaSuccess) { persist_destroy(S); return fail(ONEBIT_ERR_CUDA, "persist_create: cudaMalloc failed"); }
+        cudaMemcpy(S->lscal, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice);
+        P.lscal = S->lscal;
     }
     // ---- exchange arenas
     const size_t B = kMaxTok, nc = P.ncta;
@@ -1426,6 +1584,8 @@ void persist_destroy(PersistState* S) {
     cudaFree(S->xch[0]);
     cudaFree(S->xch[1]);
     cudaFree(S->dlayers);
+    cudaFree(S->lscal);
+    cudaFree(S->wtiled);
     cudaFree(S->dp);
     cudaFree(S->step_counter);
     cudaFree(S->abort_flag);

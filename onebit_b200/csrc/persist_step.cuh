@@ -62,6 +62,7 @@ struct Params {
     float rms_eps, ln_eps;
     double inv_H, inv_I;
     const LayerDev* layers;
+    const int* lscal;  // [L + 1][8] per-layer scalars for the parameter blocks: e_q, e_k, e_v, e_o, e_gate, e_up, max|down.h| bits, 0
     const __half* embed;
     const void* final_norm;
     const __half* lm_head;

@@ -19,6 +19,7 @@ def pytest_sessionstart(session):
     from onebit_b200 import build as _build
     try:
         _build.build()
+        _build.build_torch_ops()
     except Exception as exc:  # surfaced by the tests that need the library
         print(f"[conftest] could not build libonebit_b200.so: {exc}")
 

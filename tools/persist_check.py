@@ -106,14 +106,14 @@ def timing(config, name, batch=1, steps=64, prompt_len=16):
             t = tr[who].astype(np.int64)
             lay = t[1:1 + L]
             seg = np.diff(lay[:, :6], axis=1)  # qkv, attention, o+resid, gate/up, down+resid
-            sub = {"A_poll": lay[:, 6] - lay[:, 0], "A_mma": lay[:, 7] - lay[:, 6], "A_epi": lay[:, 1] - lay[:, 7],
+            sub = {"A_poll": lay[:, 6] - lay[:, 0], "A_wwait": lay[:, 20] - lay[:, 6], "A_mma": lay[:, 7] - lay[:, 20], "A_epi": lay[:, 1] - lay[:, 7],
                    "B_poll": lay[:, 17] - lay[:, 1], "B_rope": lay[:, 18] - lay[:, 17], "B_softmax": lay[:, 19] - lay[:, 18],
                    "B_out": lay[:, 2] - lay[:, 19],
-                   "C_poll": lay[:, 8] - lay[:, 2], "C_mma": lay[:, 9] - lay[:, 8], "C_stats": lay[:, 10] - lay[:, 9],
+                   "C_poll": lay[:, 8] - lay[:, 2], "C_wwait": lay[:, 21] - lay[:, 8], "C_mma": lay[:, 9] - lay[:, 21], "C_stats": lay[:, 10] - lay[:, 9],
                    "C_pub": lay[:, 3] - lay[:, 10],
-                   "D1_poll": lay[:, 11] - lay[:, 3], "D1_mma": lay[:, 12] - lay[:, 11], "D1_stats": lay[:, 13] - lay[:, 12],
+                   "D1_poll": lay[:, 11] - lay[:, 3], "D1_wwait": lay[:, 22] - lay[:, 11], "D1_mma": lay[:, 12] - lay[:, 22], "D1_stats": lay[:, 13] - lay[:, 12],
                    "D1_pub": lay[:, 4] - lay[:, 13],
-                   "D2_poll": lay[:, 14] - lay[:, 4], "D2_mma": lay[:, 15] - lay[:, 14], "D2_stats": lay[:, 16] - lay[:, 15],
+                   "D2_poll": lay[:, 14] - lay[:, 4], "D2_wwait": lay[:, 23] - lay[:, 14], "D2_mma": lay[:, 15] - lay[:, 23], "D2_stats": lay[:, 16] - lay[:, 15],
                    "D2_pub": lay[:, 5] - lay[:, 16]}
             o = {"per_layer_mean": [round(float(x) / 1e3, 2) for x in seg.mean(0)],
                  "layers_total": float(lay[-1, 5] - lay[0, 0]) / 1e3,
