@@ -184,10 +184,11 @@ ONEBIT_API int onebit_decoder_is_persistent(onebit_decoder* dec);
  * 2 = a step was asked to decode past max_seq_len (it wrote nothing outside the cache). */
 ONEBIT_API int onebit_decoder_status(onebit_decoder* dec, int* code);
 /* Device time stamps (ns, %globaltimer) recorded by two CTAs of the persistent step (the first and the last) during
- * the LAST step: layout [2 tracers][L + 2 rows][32 slots]. Row 0: [0] kernel start. Row 1 + l (layer l): [0] layer start,
+ * the LAST step: layout [2 tracers][L + 2 rows][160 slots]. Row 0: [0] kernel start. Row 1 + l (layer l): [0] layer start,
  * [1] q/k/v done, [2] attention done, [3] o_proj + gate/up inputs done, [4] gate/up done, [5] down_proj done; sub-stage
  * stamps: [6,7] q/k/v inputs copied / MMA done, [8,9,10] o_proj inputs / MMA / statistics exchange, [11,12,13] gate/up,
- * [14,15,16] down_proj, [17,18,19] attention inputs / cache append / softmax. Row 1 + L: [0] lm_head start, [1] step end
+ * [14,15,16] down_proj, [17,18,19] attention inputs / cache append / softmax, [20..23] weights of the stage in shared memory;
+ * [32..95] time of every CTA barrier of the layer in program order, [96..159] the source line of that barrier. Row 1 + L: [0] lm_head start, [1] step end
  * (first tracer only). Returns the number of 64-bit words written (0 when the decoder is not persistent). Synchronous. */
 ONEBIT_API int onebit_decoder_read_trace(onebit_decoder* dec, uint64_t* out, int n);
 ONEBIT_API void onebit_decoder_destroy(onebit_decoder* dec);

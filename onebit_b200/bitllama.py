@@ -216,16 +216,16 @@ class BitLlamaDecoderB200:
         return int(code.value)
 
     def read_trace(self) -> Optional[np.ndarray]:
-        """Stage time stamps (ns) of the last persistent step: array [2 tracer CTAs, L + 2, 32] (see onebit_b200.h),
+        """Stage time stamps (ns) of the last persistent step: array [2 tracer CTAs, L + 2, 192] (see onebit_b200.h),
         or None."""
         if not self.persistent:
             return None
-        n = 2 * 32 * (self.L + 2)
+        n = 2 * 192 * (self.L + 2)
         buf = np.zeros(n, dtype=np.uint64)
         got = self.lib.onebit_decoder_read_trace(self._handle, buf.ctypes.data, n)
         if got <= 0:
             return None
-        return buf.reshape(2, self.L + 2, 32)
+        return buf.reshape(2, self.L + 2, 192)
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -27,16 +27,16 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n
 
 __device__ __forceinline__ uint4 ldv4(const uint32_t* p) {
     uint4 r;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 __device__ __forceinline__ uint32_t ldv1(const uint32_t* p) {
     uint32_t r;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
-__device__ __forceinline__ void stv1(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void stv16(void* p, uint32_t v) { asm volatile("st.volatile.global.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void stv1(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v)); }
+__device__ __forceinline__ void stv16(void* p, uint32_t v) { asm volatile("st.volatile.global.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v)); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
@@ -66,12 +66,18 @@ __device__ __forceinline__ uint32_t fbits(float f) {  // publishable bit pattern
 // give-up logic of every polling loop: a protocol bug must end the kernel, not hang the GPU. The bound is a
 // wall-clock deadline for the whole step (set by every CTA at kernel start), checked every 1024 failed polls.
 __shared__ unsigned long long s_deadline;
+__shared__ unsigned long long* s_abort_info;  // trace row 0, slots 8..: who gave up first (debug aid)
+__shared__ int s_site;                        // layer * 16 + stage of the compute warps (set at stage boundaries)
 constexpr int kLmRows = 2;  // lm_head rows per ring chunk
 constexpr unsigned long long kStepBudgetNs = 400ull * 1000ull * 1000ull;
 __device__ __noinline__ bool spin_giveup_slow(int spins, int* abort_flag) {
     if (ldv1(reinterpret_cast<const uint32_t*>(abort_flag)) != 0u) return true;
     if (spins >= 1024 && gtime() > s_deadline) {
-        atomicExch(abort_flag, 1);
+        if (atomicExch(abort_flag, 1) == 0 && s_abort_info != nullptr) {
+            s_abort_info[8] = blockIdx.x;
+            s_abort_info[9] = threadIdx.x;
+            s_abort_info[10] = (unsigned long long)s_site;
+        }
         return true;
     }
     return false;
@@ -134,7 +140,7 @@ __device__ __forceinline__ uint32_t digits255(int v) {
 }
 // x' (already * input_factor), |x'| < 2^e -> packed digits of the plane-scaled 23-bit integer
 // (imma_gemv.cuh: v = q << (7-j), -q for j = 7)
-__device__ __noinline__ uint32_t quant_digits(float xp, int e, int col) {
+__device__ __forceinline__ uint32_t quant_digits(float xp, int e, int col) {
     int q = __float2int_rn(xp * ldexpf(1.0f, 22 - e));
     q = max(-(1 << 22), min(1 << 22, q));
     const int j = col & 7;
@@ -166,7 +172,7 @@ __device__ __forceinline__ float warp_max_f(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __noinline__ void put_hilo(uint32_t* p, uint32_t* pc, double v) {  // double as two publishable floats
+__device__ __forceinline__ void put_hilo(uint32_t* p, uint32_t* pc, double v) {  // double as two publishable floats
     const float hi = (float)v, lo = (float)(v - (double)hi);
     stv1(p, fbits(hi));
     stv1(p + 1, fbits(lo));
@@ -174,17 +180,29 @@ __device__ __noinline__ void put_hilo(uint32_t* p, uint32_t* pc, double v) {  //
     stv1(pc + 1, kSentF);
 }
 
-// ---- the ring of weight tiles --------------------------------------------------------------------------------
+// ---- the ring of weight tiles: fixed slots -----------------------------------------------------------------------
+// A slot is 2 * H bytes: one re-tiled 16-row tile of a K = H matrix, which is also one fp16 lm_head row. A down_proj
+// tile (K = I) takes nsD = ceil(I / H) consecutive slots, an lm_head chunk kLmRows. A chunk never straddles the ring
+// end (the slots left over are skipped, by both sides). Producer and consumers walk the same chunk sequence, each
+// with a slot counter and one parity bit per slot: the consumers' bits belong to the `full` barriers (flipped when a
+// slot is waited on as the first slot of a chunk), the producer's to the `empty` barriers (flipped for every slot it
+// takes; the consumers arrive on every slot of a chunk they release). Skipped slots see no barrier traffic at all,
+// so every barrier advances exactly one phase per use and neither side can get two phases ahead of the other.
+constexpr int kMaxSlots = 32;
 struct Ring {
-    uint32_t head, cap, seq;
-    __device__ __forceinline__ uint32_t alloc(uint32_t bytes, uint32_t& my_seq) {
-        if (head + bytes > cap) head = 0;
-        const uint32_t off = head;
-        head += bytes;
-        my_seq = seq++;
-        return off;
-    }
+    uint32_t slot, NS, phase;
 };
+__device__ __forceinline__ uint32_t ring_take(Ring& R, uint32_t n, uint32_t& skip) {
+    skip = 0;
+    if (R.slot + n > R.NS) {
+        skip = R.NS - R.slot;
+        R.slot = 0;
+    }
+    const uint32_t s = R.slot;
+    R.slot += n;
+    if (R.slot >= R.NS) R.slot = 0;
+    return s;
+}
 __device__ __forceinline__ void block_range(int nblocks, int cta, int ncta, int& b0, int& b1) {
     b0 = (int)(((long long)nblocks * cta) / ncta);
     b1 = (int)(((long long)nblocks * (cta + 1)) / ncta);
@@ -195,18 +213,26 @@ __device__ __forceinline__ void block_range(int nblocks, int cta, int ncta, int&
 // one conflict-free LDS.128 per lane and unit. `pitch` below is tile_bytes / 16 = K / 8.
 __device__ __host__ __forceinline__ int row_pitch(int kb) { return kb; }
 
-struct TileInfo {
-    uint32_t soff;     // byte offset of the tile inside the ring
-    int pslot;         // which digit set / scale the tile's rows use
-    int goff;          // element offset (parameter block) of the weight_scale of the tile's first row
-    int red_off;       // where the tile's K-group partial sums live in `red` (ints): [kgn][16][8]
-    int kgn;           // K groups of the pass the tile belongs to
+// layer-invariant description of one BitLinear stage of this CTA (built once per step, shared memory)
+enum { ST_A = 0, ST_C = 1, ST_D1 = 2, ST_D2 = 3 };
+struct StageTab {
+    int K, T;          // input width, 16-row tiles of this CTA
+    int lgKG, tpg;     // 16 warps = TG tile groups x KG = 2^lgKG K groups; tiles per group (<= 3)
+    int nsl;           // ring slots per tile
+    unsigned char pslot[kMaxTiles];  // which digit set / scale the tile's rows use
+    short goff[kMaxTiles];           // element offset (parameter block) of the weight_scale of the tile's first row
 };
-__device__ __forceinline__ int tg_of(int n) { return n >= 4 ? 4 : (n >= 2 ? 2 : 1); }
-// tiles of a stage are processed in passes that fit the ring: the whole stage if possible, else 4 (or 2) at a time
-__device__ __forceinline__ int pass_size(int T, int tile_bytes, int ring_bytes) {
-    const int fit = ring_bytes / tile_bytes - 1;
-    return T <= fit ? max(T, 1) : (fit >= 4 ? 4 : 2);
+// split of the 16 compute warps of a T-tile, `units`-unit stage: fewest (tiles per warp) x (units per warp)
+__device__ __forceinline__ void plan_split(int T, int units, int& lgKG, int& tpg) {
+    int best = 1 << 30;
+    lgKG = 4;
+    tpg = max(T, 1);
+    for (int lt = 0; lt <= 2; ++lt) {  // TG = 1, 2, 4
+        const int TG = 1 << lt, KG = kCW >> lt, tp = (max(T, 1) + TG - 1) / TG;
+        if (tp > 3) continue;
+        const int cost = tp * ((units + KG - 1) / KG);
+        if (cost < best) { best = cost; lgKG = 4 - lt; tpg = tp; }
+    }
 }
 
 // ---- shared-memory plan ---------------------------------------------------------------------------------------
@@ -221,7 +247,8 @@ struct Smem {
     double* redd;                 // [32]
     unsigned long long* q128;     // [2][kMaxTok]
     double* invs;                 // [2][kMaxTok]
-    TileInfo* tile;               // [kMaxTiles]
+    StageTab* tab;                // [4]
+    uint32_t* tslot;              // [kMaxTiles] ring slot of tile i of the current stage
     float* fscr;                  // [64]
 };
 
@@ -238,9 +265,19 @@ struct Ctx {
     Ring R;
     unsigned long long* trl;  // trace row of the current layer (tracer CTAs only, else nullptr)
     const unsigned char* pb;  // parameter block of the current layer
+    int tseq;                 // next slot of the barrier-level trace (tracer thread only)
 };
 __device__ __forceinline__ void stamp(const Ctx& c, int slot) {
     if (c.trl != nullptr && c.tid == 0) c.trl[slot] = gtime();
+}
+// barrier-level trace: slots [32, 96) hold times, [96, 160) the source line of the barrier
+__device__ __forceinline__ void csync(Ctx& c, int line) {
+    cta_sync();
+    if (c.trl != nullptr && c.tid == 0 && c.tseq < 64) {
+        c.trl[32 + c.tseq] = gtime();
+        c.trl[96 + c.tseq] = (unsigned long long)line;
+        ++c.tseq;
+    }
 }
 
 // ---- Lamport copies global -> shared ------------------------------------------------------------------------
@@ -297,97 +334,57 @@ __device__ __noinline__ void poll_copy_f(const uint32_t* __restrict__ src, uint3
     }
 }
 
-// ---- IMMA phase: this warp's share (tile group x K group) of one pass of tiles [p0, p0 + n), partial sums to `red` --
-__device__ __forceinline__ void imma_phase(const unsigned char* ring, const TileInfo* s_tile, int p0, int n, int K, int pitch,
-                                           const uint32_t* dbuf, int set_words, int M, int* red, int warp, int lane) {
-    if (n <= 0) return;
-    const int TG = tg_of(n), KG = kCW / TG;
-    const int tg = warp / KG, kg = warp - tg * KG;
-    const int tpg = (n + TG - 1) / TG;
-    const int t0 = p0 + tg * tpg, nt = min(tpg, p0 + n - t0);
-    if (nt <= 0) return;
-    const int g = lane >> 2, t4 = lane & 3, units = K >> 8;
-    const int bm = g >> 2, bd = g & 3;
-    int acc[3][2][4];
+// ---- IMMA phase: this warp's NT tiles x its K group of the stage, partial sums to `red` [tile][kg][16 rows][8] ------
+template <int NT>
+__device__ __forceinline__ void imma_phase(const unsigned char* ring, uint32_t slot_bytes, const uint32_t* tslot, const StageTab& tb, int t0,
+                                           int kg, int KG, const uint32_t* dbuf, int set_words, int M, int* red, int lane) {
+    const int K = tb.K, units = K >> 8;
+    const int g = lane >> 2, t4 = lane & 3, bm = g >> 2, bd = g & 3;
+    int acc[NT][2][4];
+    const unsigned char* wp[NT];
+    const uint32_t* bp[NT];
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int ti = 0; ti < NT; ++ti) {
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0;
-    uint32_t soff[3];
-    int psl[3];
-#pragma unroll
-    for (int ti = 0; ti < 3; ++ti) {
-        const int tt = min(t0 + ti, p0 + n - 1);
-        soff[ti] = s_tile[tt].soff + (uint32_t)(lane * 16);
-        psl[ti] = s_tile[tt].pslot;
+            for (int c = 0; c < 4; ++c) acc[ti][b][c] = 0;
+        wp[ti] = ring + (size_t)tslot[t0 + ti] * slot_bytes + lane * 16;
+        bp[ti] = dbuf + (size_t)tb.pslot[t0 + ti] * set_words + (size_t)bm * K + bd * 16 + t4 * 4;
     }
-    (void)pitch;
-    const bool uniform = psl[0] == psl[1] && psl[1] == psl[2];
-    if (uniform) {  // the common case: one digit set for all of this warp's tiles -> tiles interleaved per plane (ILP)
-        const uint32_t* bp0 = dbuf + (size_t)psl[0] * set_words + (size_t)bm * K + bd * 16 + t4 * 4;
-        for (int u = kg; u < units; u += KG) {
-            uint4 bv[4], w[3];
+    const bool have = bm < M;
+    for (int u = kg; u < units; u += KG) {
+        uint4 w[NT];
 #pragma unroll
-            for (int jp = 0; jp < 4; ++jp)
-                bv[jp] = bm < M ? *reinterpret_cast<const uint4*>(bp0 + u * 256 + jp * 64) : make_uint4(0u, 0u, 0u, 0u);
+        for (int ti = 0; ti < NT; ++ti) w[ti] = *reinterpret_cast<const uint4*>(wp[ti] + u * 512);
 #pragma unroll
-            for (int ti = 0; ti < 3; ++ti)
-                w[ti] = ti < nt ? *reinterpret_cast<const uint4*>(ring + soff[ti] + u * 512) : make_uint4(0u, 0u, 0u, 0u);
+        for (int jp = 0; jp < 4; ++jp) {
+            uint4 bv[NT];
 #pragma unroll
-            for (int jp = 0; jp < 4; ++jp)
+            for (int ti = 0; ti < NT; ++ti)
+                bv[ti] = have ? *reinterpret_cast<const uint4*>(bp[ti] + u * 256 + jp * 64) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const uint32_t mask = 0x01010101u << (2 * jp + jj);
-                    const uint32_t b0 = jj ? bv[jp].z : bv[jp].x, b1 = jj ? bv[jp].w : bv[jp].y;
+            for (int jj = 0; jj < 2; ++jj) {
+                const uint32_t mask = 0x01010101u << (2 * jp + jj);
 #pragma unroll
-                    for (int ti = 0; ti < 3; ++ti)
-                        if (ti < nt)
-                            imma16832(acc[ti][jj], plane(w[ti].x, mask), plane(w[ti].z, mask), plane(w[ti].y, mask), plane(w[ti].w, mask), b0, b1);
-                }
-        }
-    } else {
-        for (int u = kg; u < units; u += KG) {
-            uint4 bv[4];
-            int loaded = -1;
-#pragma unroll
-            for (int ti = 0; ti < 3; ++ti) {
-                if (ti < nt) {
-                    if (psl[ti] != loaded) {
-                        loaded = psl[ti];
-                        const uint32_t* bp = dbuf + (size_t)loaded * set_words + (size_t)bm * K + u * 256 + bd * 16 + t4 * 4;
-#pragma unroll
-                        for (int jp = 0; jp < 4; ++jp)
-                            bv[jp] = bm < M ? *reinterpret_cast<const uint4*>(bp + jp * 64) : make_uint4(0u, 0u, 0u, 0u);
-                    }
-                    const uint4 w = *reinterpret_cast<const uint4*>(ring + soff[ti] + u * 512);
-#pragma unroll
-                    for (int jp = 0; jp < 4; ++jp)
-#pragma unroll
-                        for (int jj = 0; jj < 2; ++jj) {
-                            const uint32_t mask = 0x01010101u << (2 * jp + jj);
-                            imma16832(acc[ti][jj], plane(w.x, mask), plane(w.z, mask), plane(w.y, mask), plane(w.w, mask),
-                                      jj ? bv[jp].z : bv[jp].x, jj ? bv[jp].w : bv[jp].y);
-                        }
-                }
+                for (int ti = 0; ti < NT; ++ti)
+                    imma16832(acc[ti][jj], plane(w[ti].x, mask), plane(w[ti].z, mask), plane(w[ti].y, mask), plane(w[ti].w, mask),
+                              jj ? bv[ti].z : bv[ti].x, jj ? bv[ti].w : bv[ti].y);
             }
         }
     }
 #pragma unroll
-    for (int ti = 0; ti < 3; ++ti) {
-        if (ti < nt) {
-            int* base = red + s_tile[t0 + ti].red_off + kg * 128 + 2 * t4;
-            *reinterpret_cast<int2*>(base + g * 8) = make_int2(acc[ti][0][0] + acc[ti][1][0], acc[ti][0][1] + acc[ti][1][1]);
-            *reinterpret_cast<int2*>(base + (g + 8) * 8) = make_int2(acc[ti][0][2] + acc[ti][1][2], acc[ti][0][3] + acc[ti][1][3]);
-        }
+    for (int ti = 0; ti < NT; ++ti) {
+        int* base = red + ((t0 + ti) * KG + kg) * 128 + 2 * t4;
+        *reinterpret_cast<int2*>(base + g * 8) = make_int2(acc[ti][0][0] + acc[ti][1][0], acc[ti][0][1] + acc[ti][1][1]);
+        *reinterpret_cast<int2*>(base + (g + 8) * 8) = make_int2(acc[ti][0][2] + acc[ti][1][2], acc[ti][0][3] + acc[ti][1][3]);
     }
 }
-// row result of the stage: t = sum_k s(n,k) x'_k for (row r of tile ti, token em), from the K-group partial sums
-__device__ __noinline__ float row_value(const int* red, const TileInfo* ti, int r, int em, long long q128, double invs) {
+// row result of the stage: t = sum_k s(n,k) x'_k for (row r of tile `tile`, token em), from the K-group partial sums
+__device__ __forceinline__ float row_value(const int* red, int tile, int KG, int r, int em, long long q128, double invs) {
     int4 a = make_int4(0, 0, 0, 0);
-    const int* p = red + ti->red_off + r * 8 + 4 * em;
-    for (int kg = 0; kg < ti->kgn; ++kg) {
+    const int* p = red + tile * KG * 128 + r * 8 + 4 * em;
+    for (int kg = 0; kg < KG; ++kg) {
         const int4 v = *reinterpret_cast<const int4*>(p + kg * 128);
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
@@ -395,23 +392,13 @@ __device__ __noinline__ float row_value(const int* red, const TileInfo* ti, int 
     return (float)((double)(q128 - 2 * V) * invs);                               // invs = 2^(e-22) / 128
 }
 
-// describe tile i of a T-tile stage (executed by thread i while every thread walks the ring allocator)
-__device__ __noinline__ void put_tile(Ctx& c, int i, int T, int pitch, uint32_t off, int pslot, int goff) {
-    TileInfo& t = c.S.tile[i];
-    t.soff = off;
-    t.pslot = pslot;
-    t.goff = goff;
-    const int ps = pass_size(T, 16 * pitch, c.ring_bytes);
-    const int p = i / ps, n = min(ps, T - p * ps);
-    t.kgn = kCW / tg_of(n);
-    t.red_off = (p * ps * (kCW / tg_of(ps)) + (i - p * ps) * t.kgn) * 128;
-}
-
-// generic BitLinear stage core: copy the input digit vectors (Lamport poll), run the IMMA passes, release the tiles.
-// `seq0`: ring sequence number of the stage's first tile (its T tiles are consecutive chunks).
-__device__ __noinline__ void stage_core(Ctx& c, int K, int pitch, int T, uint32_t seq0, int nsets, const uint32_t* x0, const uint32_t* x1, int ts) {
+// generic BitLinear stage core: copy the input digit vectors (Lamport poll), wait for the stage's weight tiles (the next
+// T chunks of the ring), run the IMMA phase, release the tiles.
+__device__ __forceinline__ void stage_core(Ctx& c, int st, int nsets, const uint32_t* x0, const uint32_t* x1, int ts) {
+    const StageTab& tb = c.S.tab[st];
+    const int K = tb.K, T = tb.T, nsl = tb.nsl;
     const int set_words = c.M * K;
-    cta_sync();  // S.tile / S.invs / S.q128 of this stage are in place, the previous stage's readers are done
+    csync(c, __LINE__);  // S.invs / S.q128 of this stage are in place, the previous stage's readers are done
     if (T > 0) {
         for (int ps = 0; ps < nsets; ++ps)
             for (int m = 0; m < c.M; ++m)
@@ -419,25 +406,50 @@ __device__ __noinline__ void stage_core(Ctx& c, int K, int pitch, int T, uint32_
                             &c.S.q128[ps * kMaxTok + m], c.abort_flag);
     }
     stamp(c, ts);
-    const int psz = pass_size(T, 16 * pitch, c.ring_bytes);
-    for (int p0 = 0; p0 < max(T, 1); p0 += psz) {
-        const int n = min(psz, T - p0);
-        if (c.warp < n && c.lane == 0) {
-            const uint32_t sq = seq0 + (uint32_t)(p0 + c.warp);
-            mbar_wait_b(&c.full[sq % kNB], (sq / kNB) & 1, c.abort_flag);
+    uint32_t myslot = 0;
+    if (nsl == 1) {  // T consecutive single-slot chunks: closed form
+        uint32_t sl = c.R.slot + (uint32_t)c.tid;
+        if (sl >= c.R.NS) sl -= c.R.NS;
+        if (c.tid < T) {
+            myslot = sl;
+            c.S.tslot[c.tid] = sl;
+            mbar_wait_b(&c.full[sl], (c.R.phase >> sl) & 1u, c.abort_flag);
         }
-        cta_sync();
-        if (p0 == 0) stamp(c, ts == 6 ? 20 : (ts == 8 ? 21 : (ts == 11 ? 22 : 23)));  // weights of the first pass are in
-        imma_phase(c.S.ring, c.S.tile, p0, n, K, pitch, c.S.dbuf, set_words, c.M, c.S.red, c.warp, c.lane);
-        cta_sync();
-        if (c.tid < n) mbar_arrive(&c.empty[(seq0 + (uint32_t)(p0 + c.tid)) % kNB]);
+        const unsigned long long bits = ((1ull << T) - 1ull) << c.R.slot;
+        c.R.phase ^= (uint32_t)((bits | (bits >> c.R.NS)) & ((1ull << c.R.NS) - 1ull));
+        c.R.slot += (uint32_t)T;
+        if (c.R.slot >= c.R.NS) c.R.slot -= c.R.NS;
+    } else {
+        for (int i = 0; i < T; ++i) {
+            uint32_t skip;
+            const uint32_t sl = ring_take(c.R, (uint32_t)nsl, skip);  // skipped slots: no barrier traffic on either side
+            if (c.tid == i) {
+                myslot = sl;
+                c.S.tslot[i] = sl;
+                mbar_wait_b(&c.full[sl], (c.R.phase >> sl) & 1u, c.abort_flag);
+            }
+            c.R.phase ^= 1u << sl;
+        }
     }
+    csync(c, __LINE__);
+    stamp(c, ts == 6 ? 20 : (ts == 8 ? 21 : (ts == 11 ? 22 : 23)));  // the stage's weights are in shared memory
+    {
+        const int KG = 1 << tb.lgKG, tg = c.warp >> tb.lgKG, kg = c.warp & (KG - 1);
+        const int t0 = tg * tb.tpg, nt = min(tb.tpg, T - t0);
+        const uint32_t slot_bytes = 2u * (uint32_t)c.H;
+        if (nt == 1) imma_phase<1>(c.S.ring, slot_bytes, c.S.tslot, tb, t0, kg, KG, c.S.dbuf, set_words, c.M, c.S.red, c.lane);
+        else if (nt == 2) imma_phase<2>(c.S.ring, slot_bytes, c.S.tslot, tb, t0, kg, KG, c.S.dbuf, set_words, c.M, c.S.red, c.lane);
+        else if (nt == 3) imma_phase<3>(c.S.ring, slot_bytes, c.S.tslot, tb, t0, kg, KG, c.S.dbuf, set_words, c.M, c.S.red, c.lane);
+    }
+    csync(c, __LINE__);
+    if (c.tid < T)
+        for (int k = 0; k < nsl; ++k) mbar_arrive(&c.empty[myslot + (uint32_t)k]);
     stamp(c, ts + 1);
 }
 
 // publish the digits of `nprob` BitLinear inputs for the owned 32-column blocks: S.stage[(m*nprob+p)*nown + col] holds
 // the four packed digits of column col; every (plane, digit) word of the B-fragment layout is assembled from 4 columns
-__device__ __noinline__ void publish32(Ctx& c, size_t xoff, size_t prob_stride, size_t tok_stride, int nprob, int nown, int col0) {
+__device__ __forceinline__ void publish32(Ctx& c, size_t xoff, size_t prob_stride, size_t tok_stride, int nprob, int nown, int col0) {
     const int nblk = nown >> 5;
     if (nblk <= 0) return;
     const int items = kMaxTok * nprob * nblk * 32;
@@ -458,7 +470,7 @@ __device__ __noinline__ void publish32(Ctx& c, size_t xoff, size_t prob_stride, 
     }
 }
 // same for 16-column blocks (stage D1): each fragment word gets a 16-bit half from this CTA
-__device__ __noinline__ void publish16(Ctx& c, size_t xoff, size_t tok_stride, int npb, int col0) {
+__device__ __forceinline__ void publish16(Ctx& c, size_t xoff, size_t tok_stride, int npb, int col0) {
     const int nown = 16 * npb, items = kMaxTok * npb * 32;
     for (int it = c.tid; it < items; it += kCT) {
         const int jd = it & 31, j = jd >> 2, d = jd & 3;
@@ -476,10 +488,10 @@ __device__ __noinline__ void publish16(Ctx& c, size_t xoff, size_t tok_stride, i
 
 // exchange of per-CTA statistics records [M][ncta][kStatW]: poll every CTA's record, then reduce in a fixed order:
 // quantity q < nq is a sum of (hi, lo) pairs, the nmax quantities after are maxima. Result: S.redd[m * (nq + nmax) + q].
-__device__ __noinline__ void stats_exchange(Ctx& c, size_t soff, int nq, int nmax) {
+__device__ __forceinline__ void stats_exchange(Ctx& c, size_t soff, int nq, int nmax) {
     for (int m = 0; m < c.M; ++m)
         poll_copy_f(c.X + soff + (size_t)m * c.ncta * kStatW, c.S.stat + (size_t)m * c.ncta * kStatW, c.ncta * kStatW / 4, c.tid, c.abort_flag);
-    cta_sync();
+    csync(c, __LINE__);
     const int per = nq + nmax;
     if (c.warp < per * c.M) {
         const int m = c.warp / per, qn = c.warp - m * per;
@@ -496,14 +508,15 @@ __device__ __noinline__ void stats_exchange(Ctx& c, size_t soff, int nq, int nma
             if (c.lane == 0) c.S.redd[c.warp] = (double)mx;
         }
     }
-    cta_sync();
+    csync(c, __LINE__);
 }
 
 // x_hat = resid * rr[token] * ln_w -> x' for q, k, v of layer l -> digits -> exchange (inputs of stage A)   (:67-81)
 // FROM_BLOCK: parameters of layer l come from the parameter block of layer l - 1 ("next layer" slices); else (layer 0,
 // once per step) straight from global memory.
 template <bool FROM_BLOCK>
-__device__ __noinline__ void publish_qkv_inputs(Ctx& c, const Params& P, int l, float resid, const float* rr) {
+__device__ __noinline__ void publish_qkv_inputs(Ctx& cref, const Params& P, int l, float resid, const float* rr) {
+    Ctx c = cref;  // scalar-replaced local copy: the fields live in registers, not behind a pointer
     if (c.ownerC) {
         float lw, hq, hk, hv;
         int eq, ek, ev;
@@ -523,31 +536,42 @@ __device__ __noinline__ void publish_qkv_inputs(Ctx& c, const Params& P, int l, 
         c.S.stage[(size_t)(c.om * 3 + 1) * c.nownC + c.oc] = quant_digits(xh * hk, ek, col);
         c.S.stage[(size_t)(c.om * 3 + 2) * c.nownC + c.oc] = quant_digits(xh * hv, ev, col);
     }
-    cta_sync();
+    csync(c, __LINE__);
     publish32(c, (size_t)l * P.per_layer + P.o_xA, (size_t)kMaxTok * c.H, (size_t)c.H, 3, c.nownC, c.colC0);
+    cref.R = c.R;
+    cref.tseq = c.tseq;
+}
+
+// x_hat = RMSNorm(post_attention_layernorm) of the updated stream -> x' for gate / up -> digits -> exchange (stage D1 inputs)
+__device__ __noinline__ void publish_gu_inputs(Ctx& cref, const Params& P, int l, float resid, const float* rr) {
+    Ctx c = cref;
+    if (c.ownerC) {
+        const int col = c.colC0 + c.oc;
+        const float xh = resid * rr[c.om] * pbf(c.pb, PB_lnP, c.oc, c.pdt);
+        c.S.stage[(size_t)(c.om * 2 + 0) * c.nownC + c.oc] = quant_digits(xh * pbf(c.pb, PB_hg, c.oc, c.pdt), pbi(c.pb, 0, 4), col);
+        c.S.stage[(size_t)(c.om * 2 + 1) * c.nownC + c.oc] = quant_digits(xh * pbf(c.pb, PB_hu, c.oc, c.pdt), pbi(c.pb, 0, 5), col);
+    }
+    csync(c, __LINE__);
+    publish32(c, (size_t)l * P.per_layer + P.o_xD1, (size_t)kMaxTok * c.H, (size_t)c.H, 2, c.nownC, c.colC0);
+    cref.tseq = c.tseq;
 }
 
 // stages C / D2 share their shape: rows of o_proj / down_proj owned as 32-row blocks, then
 // x <- x + LayerNorm(g*t) (:912 / :918) and the RMSNorm factor of the next BitLinear group (:67-81), all from ONE
 // exchange of five per-CTA sums (sum u, sum u^2, sum r, sum r^2, sum r*u).
-__device__ __noinline__ void residual_stage(Ctx& c, const Params& P, int gbase_el, int K, int pitch, const uint32_t* xin0, size_t o_stat,
-                                            float* resid_io, float* rr_out /*[M]*/, int ts) {
-    const int T = c.nownC >> 4;
-    const uint32_t seq0 = c.R.seq;
-    for (int i = 0; i < T; ++i) {
-        uint32_t seq;
-        const uint32_t off = c.R.alloc(16u * pitch, seq);
-        if (c.tid == i) put_tile(c, i, T, pitch, off, 0, gbase_el + 16 * i);
-    }
-    stage_core(c, K, pitch, T, seq0, 1, xin0, xin0, ts);
+__device__ __noinline__ void residual_stage(Ctx& cref, const Params& P, int st, const uint32_t* xin0, size_t o_stat, float* resid_io,
+                                            float* rr_out /*[M]*/, int ts) {
+    Ctx c = cref;  // scalar-replaced local copy: the fields live in registers, not behind a pointer
+    stage_core(c, st, 1, xin0, xin0, ts);
     float u = 0.f, resid = *resid_io;
     if (c.ownerC) {
-        const TileInfo* ti = &c.S.tile[c.oc >> 4];
-        u = row_value(c.S.red, ti, c.oc & 15, c.om, (long long)c.S.q128[c.om], c.S.invs[c.om]) * pbf(c.pb, ti->goff, c.oc & 15, c.pdt);
+        const StageTab& tb = c.S.tab[st];
+        u = row_value(c.S.red, c.oc >> 4, 1 << tb.lgKG, c.oc & 15, c.om, (long long)c.S.q128[c.om], c.S.invs[c.om]) *
+            pbf(c.pb, tb.goff[c.oc >> 4], c.oc & 15, c.pdt);
         c.S.u[c.om * 192 + c.oc] = u;
         c.S.u[c.om * 192 + 96 + c.oc] = resid;
     }
-    cta_sync();
+    csync(c, __LINE__);
     if (c.tid < 2 * kMaxTok) c.S.q128[c.tid] = 0ull;
     if (c.warp < kMaxTok) {  // this CTA's five sums per token
         const int m = c.warp;
@@ -585,28 +609,21 @@ __device__ __noinline__ void residual_stage(Ctx& c, const Params& P, int gbase_e
         c.S.fscr[kMaxTok + c.tid] = mean;
         c.S.fscr[2 * kMaxTok + c.tid] = rstd;
     }
-    cta_sync();
+    csync(c, __LINE__);
     if (c.ownerC) *resid_io = resid + (u - c.S.fscr[kMaxTok + c.om]) * c.S.fscr[2 * kMaxTok + c.om];
     for (int m = 0; m < c.M; ++m) rr_out[m] = c.S.fscr[m];
+    cref.R = c.R;
+    cref.tseq = c.tseq;
 }
 
 // stage A: q, k, v = BitLinear(RMSNorm(x)) (:522-524) — publishes raw g*t and per-CTA LayerNorm partials
-__device__ __noinline__ void stage_qkv(Ctx& c, const Params& P, int l, int a_b0, int a_b1, const int* s_pos) {
-    const int H = c.H, tH = H >> 4, pitchH = row_pitch(H >> 3);
+__device__ __noinline__ void stage_qkv(Ctx& cref, const Params& P, int l, int a_b0, int a_b1, const int* s_pos) {
+    Ctx c = cref;  // scalar-replaced local copy: the fields live in registers, not behind a pointer
+    const int H = c.H, tH = H >> 4;
     const int gt0 = 2 * a_b0, gt1 = 2 * a_b1, T = gt1 - gt0;
     const int p_lo = gt0 / tH, nsets = (gt1 - 1) / tH - p_lo + 1;
     uint32_t* XL = c.X + (size_t)l * P.per_layer;
     uint32_t* XLc = c.Xc + (size_t)l * P.per_layer;
-    const uint32_t seq0 = c.R.seq;
-    for (int i = 0; i < T; ++i) {
-        uint32_t seq;
-        const uint32_t off = c.R.alloc(16u * pitchH, seq);
-        if (c.tid == i) {
-            const int gt = gt0 + i, prob = gt / tH, row0 = (gt - prob * tH) * 16;
-            (void)row0;
-            put_tile(c, i, T, pitchH, off, prob - p_lo, PB_gA + 16 * i);
-        }
-    }
     if (c.tid < 2 * kMaxTok) c.S.invs[c.tid] = pow2d(pbi(c.pb, 0, min(p_lo + c.tid / kMaxTok, 2)) - 29);
     // attention CTAs: pull this layer's cached K/V rows of their (sequence, head) towards L2
     if (c.cta < P.heads * c.M) {
@@ -618,22 +635,23 @@ __device__ __noinline__ void stage_qkv(Ctx& c, const Params& P, int l, int a_b0,
             prefetch_l2(reinterpret_cast<const char*>(P.vcache + base) + (size_t)i * 128);
         }
     }
-    stage_core(c, H, pitchH, T, seq0, nsets, XL + P.o_xA + (size_t)p_lo * kMaxTok * H, XL + P.o_xA + (size_t)min(p_lo + 1, 2) * kMaxTok * H, 6);
+    stage_core(c, ST_A, nsets, XL + P.o_xA + (size_t)p_lo * kMaxTok * H, XL + P.o_xA + (size_t)min(p_lo + 1, 2) * kMaxTok * H, 6);
     const int Rr = 16 * T;
     if (c.tid < Rr * kMaxTok) {
         const int em = c.tid / Rr, er = c.tid - em * Rr;
         const int gt = gt0 + (er >> 4), prob = gt / tH, row = (gt - prob * tH) * 16 + (er & 15);
         const size_t a = P.o_qkv + ((size_t)em * 3 + prob) * H + row;
         if (em < c.M) {
-            const TileInfo* ti = &c.S.tile[er >> 4];
-            const float u = row_value(c.S.red, ti, er & 15, em, (long long)c.S.q128[ti->pslot * kMaxTok + em], c.S.invs[ti->pslot * kMaxTok + em]) *
-                            pbf(c.pb, ti->goff, er & 15, c.pdt);
+            const StageTab& tb = c.S.tab[ST_A];
+            const int ps = tb.pslot[er >> 4];
+            const float u = row_value(c.S.red, er >> 4, 1 << tb.lgKG, er & 15, em, (long long)c.S.q128[ps * kMaxTok + em], c.S.invs[ps * kMaxTok + em]) *
+                            pbf(c.pb, tb.goff[er >> 4], er & 15, c.pdt);
             c.S.u[em * 192 + er] = u;
             stv1(XL + a, fbits(u));
         }
         if (em < c.max_batch) stv1(XLc + a, kSentF);
     }
-    cta_sync();
+    csync(c, __LINE__);
     if (c.tid < 2 * kMaxTok) c.S.q128[c.tid] = 0ull;
     if (c.warp < 3 * kMaxTok) {  // per-(token, projection) partial (sum, sum of squares) of this CTA's rows
         const int m = c.warp / 3, p = c.warp - 3 * m;
@@ -657,11 +675,14 @@ __device__ __noinline__ void stage_qkv(Ctx& c, const Params& P, int l, int a_b0,
             }
         }
     }
+    cref.R = c.R;
+    cref.tseq = c.tseq;
 }
 
 // stage B: attention for one new token per sequence (:536-563): LayerNorm of q/k/v (bitnet.py:118) from the partials,
 // RoPE (:176-181), cache append, fp32 online softmax over the cache, digits of o_proj's input
-__device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, const int* s_pos) {
+__device__ __noinline__ void stage_attention(Ctx& cref, const Params& P, int l, const int* s_pos) {
+    Ctx c = cref;  // scalar-replaced local copy: the fields live in registers, not behind a pointer
     const int H = c.H, tid = c.tid, lane = c.lane, warp = c.warp, ncta = c.ncta;
     uint32_t* XL = c.X + (size_t)l * P.per_layer;
     uint32_t* XLc = c.Xc + (size_t)l * P.per_layer;
@@ -691,7 +712,7 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
         }
         *reinterpret_cast<uint4*>(raw + p * 128 + 4 * i) = v;
     }
-    cta_sync();
+    csync(c, __LINE__);
     if (warp < 6) {  // (projection, sum | sumsq): fixed-order reduction over the CTAs
         const int p = warp >> 1, which = warp & 1;
         const float* st = reinterpret_cast<const float*>(c.S.stat) + (size_t)p * ncta * 4 + 2 * which;
@@ -700,10 +721,10 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
         s = warp_sum_d(s);
         if (lane == 0) c.S.redd[warp] = s;
     }
-    cta_sync();
+    csync(c, __LINE__);
     stamp(c, 17);
     if (tid < 3) ln_finish(c.S.redd[2 * tid], c.S.redd[2 * tid + 1], P.inv_H, P.ln_eps, &c.S.fscr[2 * tid], &c.S.fscr[2 * tid + 1]);
-    cta_sync();
+    csync(c, __LINE__);
     __half* kc = P.kcache + ((((size_t)l * P.max_batch + am) * P.heads + ah) * P.max_seq) * kHeadDim;
     __half* vc = P.vcache + ((((size_t)l * P.max_batch + am) * P.heads + ah) * P.max_seq) * kHeadDim;
     if (tid < kHeadDim) {
@@ -722,7 +743,7 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
         sk[d] = __half2float(kh);
         sv[d] = __half2float(vh);
     }
-    cta_sync();
+    csync(c, __LINE__);
     stamp(c, 18);
     {   // each warp: online softmax over positions warp, warp+16, ...; lane holds dims 4*lane .. 4*lane+3
         const float4 qv = *reinterpret_cast<const float4*>(sq + 4 * lane);
@@ -771,7 +792,7 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
         if (lane == 0) { pw[0] = mx; pw[1] = lsum; }
         *reinterpret_cast<float4*>(pw + 4 + 4 * lane) = o;
     }
-    cta_sync();
+    csync(c, __LINE__);
     stamp(c, 19);
     if (tid < kHeadDim) {
         float mx = -INFINITY;
@@ -786,7 +807,7 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
         const int col = ah * kHeadDim + tid;
         c.S.stage[tid] = quant_digits((num / den) * pbf(c.pb, PB_hO, tid, c.pdt), pbi(c.pb, 0, 3), col);
     }
-    cta_sync();
+    csync(c, __LINE__);
     if (tid < 128) {
         const int blk = tid >> 5, jd = tid & 31, j = jd >> 2, d = jd & 3;
         const uint32_t* sp = c.S.stage + blk * 32 + j;
@@ -796,37 +817,31 @@ __device__ __noinline__ void stage_attention(Ctx& c, const Params& P, int l, con
         stv1(XL + a, word);
         stv1(XLc + a, kSentD);
     }
+    cref.R = c.R;
+    cref.tseq = c.tseq;
 }
 
 // stage D1: gate, up (:257) — 16 gate rows + 16 up rows of the same columns live in the same CTA, so
 // silu(LN(gate)) * LN(up) * input_factor(down) is finished by the owner after ONE exchange of sums and bounds
-__device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d_b0, int d_b1) {
-    const int H = c.H, I = c.I, pitchH = row_pitch(H >> 3), tid = c.tid, lane = c.lane, warp = c.warp;
-    (void)I;
+__device__ __noinline__ void stage_gate_up(Ctx& cref, const Params& P, int l, int d_b0, int d_b1) {
+    Ctx c = cref;  // scalar-replaced local copy: the fields live in registers, not behind a pointer
+    const int H = c.H, tid = c.tid, lane = c.lane, warp = c.warp;
     uint32_t* XL = c.X + (size_t)l * P.per_layer;
     uint32_t* XLc = c.Xc + (size_t)l * P.per_layer;
     const int npb = d_b1 - d_b0, T = 2 * npb, nown = 16 * npb, col0 = 16 * d_b0;
-    const uint32_t seq0 = c.R.seq;
-    for (int i = 0; i < T; ++i) {
-        uint32_t seq;
-        const uint32_t off = c.R.alloc(16u * pitchH, seq);
-        if (tid == i) {
-            const bool up = i >= npb;
-            put_tile(c, i, T, pitchH, off, up ? 1 : 0, up ? PB_gU + 16 * (i - npb) : PB_gG + 16 * i);
-        }
-    }
     if (tid < 2 * kMaxTok) c.S.invs[tid] = pow2d(pbi(c.pb, 0, 4 + tid / kMaxTok) - 29);
-    stage_core(c, H, pitchH, T, seq0, 2, XL + P.o_xD1, XL + P.o_xD1 + (size_t)kMaxTok * H, 11);
+    stage_core(c, ST_D1, 2, XL + P.o_xD1, XL + P.o_xD1 + (size_t)kMaxTok * H, 11);
     const int Rr = 16 * T;
     if (Rr > 0) {
         const int em = tid / Rr, er = tid - em * Rr;
         if (em < c.M) {
-            const TileInfo* ti = &c.S.tile[er >> 4];
-            c.S.u[em * 192 + er] = row_value(c.S.red, ti, er & 15, em, (long long)c.S.q128[ti->pslot * kMaxTok + em], c.S.invs[ti->pslot * kMaxTok + em]) *
-                                   pbf(c.pb, ti->goff, er & 15, c.pdt);
+            const StageTab& tb = c.S.tab[ST_D1];
+            const int ps = tb.pslot[er >> 4];
+            c.S.u[em * 192 + er] = row_value(c.S.red, er >> 4, 1 << tb.lgKG, er & 15, em, (long long)c.S.q128[ps * kMaxTok + em], c.S.invs[ps * kMaxTok + em]) *
+                                   pbf(c.pb, tb.goff[er >> 4], er & 15, c.pdt);
         }
     }
-    cta_sync();
+    csync(c, __LINE__);
     if (tid < 2 * kMaxTok) c.S.q128[tid] = 0ull;
     const bool ownerD = tid < nown * c.M;
     const int dm = ownerD ? tid / nown : 0, dc = ownerD ? tid - dm * nown : 0;
@@ -880,37 +895,47 @@ __device__ __noinline__ void stage_gate_up(Ctx& c, const Params& P, int l, int d
         reinterpret_cast<int*>(f)[4] = e;
         c.S.invs[tid] = pow2d(e - 29);  // scale of down_proj's input digits (pslot 0)
     }
-    cta_sync();
+    csync(c, __LINE__);
     if (ownerD) {
         const float* f = c.S.fscr + dm * 8;
         const float gh = (gv - f[0]) * f[1], uh = (uv - f[2]) * f[3];
         const float act = __fdiv_rn(gh, 1.0f + expf(-gh)) * uh;  // act_fn(gate) * up, :257
         c.S.stage[dm * nown + dc] = quant_digits(act * hd, reinterpret_cast<const int*>(f)[4], col0 + dc);
     }
-    cta_sync();
-    publish16(c, (size_t)l * P.per_layer + P.o_xD2, (size_t)I, npb, col0);
+    csync(c, __LINE__);
+    publish16(c, (size_t)l * P.per_layer + P.o_xD2, (size_t)c.I, npb, col0);
+    cref.R = c.R;
+    cref.tseq = c.tseq;
 }
 
-// lm_head (:1610-1611) + greedy argmax (generation/utils.py:2540): one fp16 row per ring chunk, one warp per row
-__device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, int v_b1, float* __restrict__ logits, const int* s_pos,
+// lm_head (:1610-1611) + greedy argmax (generation/utils.py:2540): kLmRows fp16 rows per ring chunk, one warp per chunk
+__device__ __noinline__ void stage_lm_head(Ctx& cref, const Params& P, int v_b0, int v_b1, float* __restrict__ logits, const int* s_pos,
                                            unsigned long long step, unsigned long long* tr) {
+    Ctx c = cref;  // scalar-replaced local copy: the fields live in registers, not behind a pointer
     const int H = c.H, M = c.M, tid = c.tid, lane = c.lane, warp = c.warp, ncta = c.ncta;
     uint32_t* Xt = c.X + (size_t)P.L * P.per_layer;
     uint32_t* Xtc = c.Xc + (size_t)P.L * P.per_layer;
     uint32_t* xs = c.S.dbuf;  // [M][H/2] half2 words
     for (int m = 0; m < M; ++m) poll_copy_f(Xt + P.o_xfin + (size_t)m * (H / 2), xs + (size_t)m * (H / 2), H / 8, tid, c.abort_flag);
-    cta_sync();
+    csync(c, __LINE__);
     float best[kMaxTok];
     int bidx[kMaxTok];
 #pragma unroll
     for (int m = 0; m < kMaxTok; ++m) { best[m] = -INFINITY; bidx[m] = 0x7fffffff; }
     const int nch = H / 8;  // uint4 chunks per row
-    for (int v0 = v_b0; v0 < v_b1; v0 += kLmRows) {
+    // chunks of kLmRows (= 2) rows = 2 slots, starting on an even slot of an even-sized ring: never straddle the end.
+    // Chunk j sits at slot (s0 + 2 (j mod hs)) mod NS, hs = NS / 2 <= 16. Warp w < hs owns slot pair w for the whole
+    // stage (chunks w, w + hs, ...): a barrier is then always waited on by the same warp, one phase at a time (a second
+    // warp sharing the slot could run two phases ahead and be fooled by the parity test).
+    if (c.R.slot & 1u) c.R.slot = c.R.slot + 1u >= c.R.NS ? 0u : c.R.slot + 1u;  // (the producer skips the same slot)
+    const uint32_t hs = c.R.NS >> 1;
+    uint32_t sl = c.R.slot + 2u * (uint32_t)warp;
+    if (sl >= c.R.NS) sl -= c.R.NS;
+    uint32_t par = (c.R.phase >> sl) & 1u;
+    for (int v0 = v_b0 + kLmRows * warp; (uint32_t)warp < hs && v0 < v_b1; v0 += kLmRows * (int)hs, par ^= 1u) {
         const int nr = min(kLmRows, v_b1 - v0);
-        uint32_t seq;
-        const uint32_t off = c.R.alloc((uint32_t)(nr * 2 * H), seq);
-        if ((int)(seq % kCW) != warp) continue;
-        mbar_wait_b(&c.full[seq % kNB], (seq / kNB) & 1, c.abort_flag);
+        const uint32_t off = sl * (uint32_t)(2 * H);
+        mbar_wait_b(&c.full[sl], par, c.abort_flag);
         float acc[kLmRows][kMaxTok];
 #pragma unroll
         for (int r = 0; r < kLmRows; ++r)
@@ -942,7 +967,7 @@ __device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, in
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&c.empty[seq % kNB]);
+        if (lane < kLmRows) mbar_arrive(&c.empty[sl + (uint32_t)lane]);
 #pragma unroll
         for (int r = 0; r < kLmRows; ++r) {
             if (r < nr) {
@@ -962,7 +987,7 @@ __device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, in
     int* si = reinterpret_cast<int*>(c.S.fscr + kCW * kMaxTok);  // [kCW][kMaxTok] indices
     if (lane == 0)
         for (int m = 0; m < kMaxTok; ++m) { sb[warp * kMaxTok + m] = best[m]; si[warp * kMaxTok + m] = bidx[m]; }
-    cta_sync();
+    csync(c, __LINE__);
     if (tid < kMaxTok && tid < c.max_batch) {
         const int m = tid;
         const size_t a = P.o_amax + ((size_t)m * ncta + c.cta) * 2;
@@ -982,7 +1007,7 @@ __device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, in
     }
     if (c.cta == 0) {
         poll_copy_f(Xt + P.o_amax, c.S.stat, M * ncta * 2 / 4, tid, c.abort_flag);  // ncta even: whole uint4s
-        cta_sync();
+        csync(c, __LINE__);
         if (tid < M) {
             const int m = tid;
             float b = -INFINITY;
@@ -995,13 +1020,15 @@ __device__ __noinline__ void stage_lm_head(Ctx& c, const Params& P, int v_b0, in
             P.ids[m] = bi == 0x7fffffff ? 0 : bi;
             P.pos[m] = s_pos[m] + 1;
         }
-        cta_sync();
+        csync(c, __LINE__);
         if (tid == 0) {
             tr[1] = gtime();
             __threadfence();
             *P.step_counter = step + 1ull;
         }
     }
+    cref.R = c.R;
+    cref.tseq = c.tseq;
 }
 
 // TMA producer warp: walks the static schedule of this CTA's weight tiles, independent of the dependency chain.
@@ -1013,28 +1040,24 @@ __device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_
                                            int v_b1) {
     const int H = P.H, I = P.I, tH = H >> 4, L = P.L;
     const uint32_t tileH = 2u * (uint32_t)H, tileI = 2u * (uint32_t)I;  // bytes of a re-tiled 16-row tile
+    const uint32_t slot_bytes = 2u * (uint32_t)H, nsD = (uint32_t)((I + H - 1) / H);
     Ring R;
-    R.head = 0; R.cap = (uint32_t)ring_bytes; R.seq = 0;
-    uint32_t q_tail = 0;  // oldest unreleased chunk
-    uint32_t my_off = 0, my_sz = 0, my_q = 0xFFFFFFFFu;
+    R.slot = 0; R.NS = (uint32_t)ring_bytes / slot_bytes; R.phase = 0xFFFFFFFFu;  // parity 1: a fresh barrier passes at once
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    auto issue = [&](const uint8_t* src, uint32_t bytes) -> bool {
-        uint32_t seq;
-        const uint32_t off = R.alloc(bytes, seq);
-        // wait until a barrier pair and the region are free: every outstanding chunk that overlaps the new region must
-        // have been released, and chunks are released in allocation order. Lane i remembers the chunk in barrier slot i.
-        uint32_t need = seq >= (uint32_t)kNB ? seq - (uint32_t)kNB + 1u : 0u;
-        const bool ov = my_q != 0xFFFFFFFFu && my_q >= q_tail && my_q < seq && !(my_off + my_sz <= off || off + bytes <= my_off);
-        need = max(need, __reduce_max_sync(0xffffffffu, ov ? my_q + 1u : 0u));
-        while (q_tail < need) {
-            if (!mbar_wait_b(&s_empty[q_tail % kNB], (q_tail / kNB) & 1, P.abort_flag)) return false;
-            ++q_tail;
-        }
-        if (lane == (int)(seq % kNB)) { my_off = off; my_sz = bytes; my_q = seq; }
+    auto take_empty = [&](uint32_t sl) -> bool {  // the previous occupant of the slot (if any) has been released
+        if (!mbar_wait_b(&s_empty[sl], (R.phase >> sl) & 1u, P.abort_flag)) return false;
+        R.phase ^= 1u << sl;
+        return true;
+    };
+    auto issue = [&](const uint8_t* src, uint32_t bytes, uint32_t nslots) -> bool {
+        uint32_t skip;
+        const uint32_t sl = ring_take(R, nslots, skip);  // skipped slots: no barrier traffic on either side
+        for (uint32_t k = 0; k < nslots; ++k)
+            if (!take_empty(sl + k)) return false;
         if (lane == 0) {
-            mbar_expect_tx(&s_full[seq % kNB], bytes);
-            bulk_g2s_hint(smem_raw + off, src, bytes, &s_full[seq % kNB], pol);
+            mbar_expect_tx(&s_full[sl], bytes);
+            bulk_g2s_hint(smem_raw + (size_t)sl * slot_bytes, src, bytes, &s_full[sl], pol);
         }
         __syncwarp();
         return true;
@@ -1090,16 +1113,17 @@ __device__ __noinline__ void producer_loop(const Params& P, unsigned char* smem_
         for (int gt = 2 * a_b0; gt < 2 * a_b1; ++gt) {
             const int prob = gt / tH, lt = gt - prob * tH;
             const uint8_t* w = prob == 0 ? Ly.q.w : (prob == 1 ? Ly.k.w : Ly.v.w);
-            if (!issue(w + (size_t)lt * tileH, tileH)) return;
+            if (!issue(w + (size_t)lt * tileH, tileH, 1u)) return;
         }
-        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.o.w + (size_t)t * tileH, tileH)) return;
-        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.gate.w + (size_t)pb * tileH, tileH)) return;
-        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.up.w + (size_t)pb * tileH, tileH)) return;
-        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.down.w + (size_t)t * tileI, tileI)) return;
+        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.o.w + (size_t)t * tileH, tileH, 1u)) return;
+        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.gate.w + (size_t)pb * tileH, tileH, 1u)) return;
+        for (int pb = d_b0; pb < d_b1; ++pb) if (!issue(Ly.up.w + (size_t)pb * tileH, tileH, 1u)) return;
+        for (int t = 2 * c_b0; t < 2 * c_b1; ++t) if (!issue(Ly.down.w + (size_t)t * tileI, tileI, nsD)) return;
     }
+    if (R.slot & 1u) R.slot = R.slot + 1u >= R.NS ? 0u : R.slot + 1u;  // lm_head chunks start on an even slot (see stage_lm_head)
     for (int v = v_b0; v < v_b1; v += kLmRows) {  // lm_head rows are contiguous: kLmRows rows per chunk, one bulk copy
         const int nr = min(kLmRows, v_b1 - v);
-        if (!issue(reinterpret_cast<const uint8_t*>(P.lm_head + (size_t)v * H), (uint32_t)(nr * 2 * H))) return;
+        if (!issue(reinterpret_cast<const uint8_t*>(P.lm_head + (size_t)v * H), (uint32_t)(nr * 2 * H), (uint32_t)kLmRows)) return;
     }
 }
 
@@ -1112,7 +1136,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in, float* __restrict__ logits, int M,
             int ring_bytes, int dbuf_bytes) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[kNB], s_empty[kNB], s_pfull[2], s_pempty[2];
+    __shared__ __align__(8) uint64_t s_full[kMaxSlots], s_empty[kMaxSlots], s_pfull[2], s_pempty[2];
     __shared__ Params P;
     __shared__ int s_tok[kMaxTok], s_pos[kMaxTok];
 
@@ -1125,7 +1149,9 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
     }
     if (tid == 0) {
         s_deadline = gtime() + kStepBudgetNs;
-        for (int i = 0; i < kNB; ++i) {
+        s_abort_info = Pg->trace;
+        s_site = -1;
+        for (int i = 0; i < kMaxSlots; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 1);
         }
@@ -1165,11 +1191,12 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         c.S.redd = reinterpret_cast<double*>(p); p += 32 * 8;
         c.S.q128 = reinterpret_cast<unsigned long long*>(p); p += 2 * kMaxTok * 8;
         c.S.invs = reinterpret_cast<double*>(p); p += 2 * kMaxTok * 8;
-        c.S.tile = reinterpret_cast<TileInfo*>(p); p += kMaxTiles * sizeof(TileInfo);
+        c.S.tab = reinterpret_cast<StageTab*>(p); p += 4 * sizeof(StageTab);
+        c.S.tslot = reinterpret_cast<uint32_t*>(p); p += kMaxTiles * 4;
         c.S.fscr = reinterpret_cast<float*>(p);
     }
     c.full = s_full; c.empty = s_empty; c.abort_flag = P.abort_flag;
-    c.R.head = 0; c.R.cap = (uint32_t)ring_bytes; c.R.seq = 0;
+    c.R.slot = 0; c.R.NS = (uint32_t)ring_bytes / (2u * (uint32_t)H); c.R.phase = 0u;
     const unsigned long long step = *P.step_counter;
     const int par = (int)(step & 1ull);
     c.X = P.xch[par];
@@ -1182,6 +1209,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
     unsigned long long* trace = who >= 0 ? P.trace + (size_t)who * (L + 2) * kTracePoints : nullptr;
     const bool tracer = who >= 0 && tid == 0;
     c.trl = nullptr;
+    c.tseq = 0;
     if (tid < kMaxTok) {
         long long id = tid < M ? ids_in[tid] : 0;
         id = id < 0 ? 0 : (id >= P.V ? P.V - 1 : id);
@@ -1194,7 +1222,24 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         s_pos[tid] = ps;
     }
     if (tid < 2 * kMaxTok) c.S.q128[tid] = 0ull;
-    cta_sync();
+    if (tid < 4) {  // the four layer-invariant stage descriptions of this CTA
+        StageTab& tb = c.S.tab[tid];
+        const int tH = H >> 4, npb = d_b1 - d_b0;
+        tb.K = tid == ST_D2 ? I : H;
+        tb.T = tid == ST_A ? 2 * (a_b1 - a_b0) : (tid == ST_D1 ? 2 * npb : 2 * (c_b1 - c_b0));
+        tb.nsl = tid == ST_D2 ? (I + H - 1) / H : 1;
+        plan_split(tb.T, tb.K >> 8, tb.lgKG, tb.tpg);
+        for (int i = 0; i < tb.T; ++i) {
+            int ps = 0, go = 0;
+            if (tid == ST_A) { ps = (2 * a_b0 + i) / tH - (2 * a_b0) / tH; go = PB_gA + 16 * i; }
+            else if (tid == ST_C) { go = PB_gO + 16 * i; }
+            else if (tid == ST_D1) { ps = i >= npb ? 1 : 0; go = i >= npb ? PB_gU + 16 * (i - npb) : PB_gG + 16 * i; }
+            else { go = PB_gDn + 16 * i; }
+            tb.pslot[i] = (unsigned char)ps;
+            tb.goff[i] = (short)go;
+        }
+    }
+    csync(c, __LINE__);
     if (tracer) trace[0] = gtime();
 
     float resid = 0.f;
@@ -1215,11 +1260,11 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
             }
             const double pd = warp_sum_d((double)part);
             if (lane == 0) c.S.redd[warp] = pd;
-            cta_sync();
+            csync(c, __LINE__);
             double tot = 0.0;
             for (int w = 0; w < kCW; ++w) tot += c.S.redd[w];
             rr[m] = rsqrtf((float)(tot / (double)H) + P.rms_eps);
-            cta_sync();
+            csync(c, __LINE__);
             if (c.ownerC && c.om == m) resid = __half2float(erow[c.colC0 + c.oc]);
         }
         publish_qkv_inputs<false>(c, P, 0, resid, rr);
@@ -1230,39 +1275,38 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         unsigned long long* tr = trace + (size_t)(1 + l) * kTracePoints;
         c.trl = who >= 0 ? tr : nullptr;
         c.pb = c.S.pbuf + (size_t)(l & 1) * kPBBytes;
+        c.tseq = 0;
+        if (tid == 0) s_site = l * 16 + 0;
         if (tracer) tr[0] = gtime();
         // the layer's parameter block has long arrived (the producer runs a layer ahead); the first readers are the
         // threads that set the stage scales, everybody else reads it after a CTA barrier
         if (tid < 2 * kMaxTok) mbar_wait_b(&s_pfull[l & 1], (l >> 1) & 1, c.abort_flag);
         stage_qkv(c, P, l, a_b0, a_b1, s_pos);
+        if (tid == 0) s_site = l * 16 + 1;
         if (tracer) tr[1] = gtime();
         stage_attention(c, P, l, s_pos);
+        if (tid == 0) s_site = l * 16 + 2;
         if (tracer) tr[2] = gtime();
         {   // stage C: o_proj (:580) + residual + post_attention_layernorm -> digits of gate / up inputs
             if (tid < kMaxTok) c.S.invs[tid] = pow2d(pbi(c.pb, 0, 3) - 29);
             float rr[kMaxTok];
-            residual_stage(c, P, PB_gO, H, row_pitch(H >> 3), c.X + lbase + P.o_xC, lbase + P.o_cst, &resid, rr, 8);
-            if (c.ownerC) {
-                const int col = c.colC0 + c.oc;
-                const float xh = resid * rr[c.om] * pbf(c.pb, PB_lnP, c.oc, c.pdt);
-                c.S.stage[(size_t)(c.om * 2 + 0) * c.nownC + c.oc] = quant_digits(xh * pbf(c.pb, PB_hg, c.oc, c.pdt), pbi(c.pb, 0, 4), col);
-                c.S.stage[(size_t)(c.om * 2 + 1) * c.nownC + c.oc] = quant_digits(xh * pbf(c.pb, PB_hu, c.oc, c.pdt), pbi(c.pb, 0, 5), col);
-            }
-            cta_sync();
-            publish32(c, lbase + P.o_xD1, (size_t)kMaxTok * H, (size_t)H, 2, c.nownC, c.colC0);
+            residual_stage(c, P, ST_C, c.X + lbase + P.o_xC, lbase + P.o_cst, &resid, rr, 8);
+            publish_gu_inputs(c, P, l, resid, rr);
         }
+        if (tid == 0) s_site = l * 16 + 3;
         if (tracer) tr[3] = gtime();
         stage_gate_up(c, P, l, d_b0, d_b1);
+        if (tid == 0) s_site = l * 16 + 4;
         if (tracer) tr[4] = gtime();
         {   // stage D2: down_proj (:257) + residual (:918) + the next layer's input_layernorm (or the final norm, :1315)
             float rr[kMaxTok];
-            residual_stage(c, P, PB_gDn, I, row_pitch(I >> 3), c.X + lbase + P.o_xD2, lbase + P.o_d2st, &resid, rr, 14);
+            residual_stage(c, P, ST_D2, c.X + lbase + P.o_xD2, lbase + P.o_d2st, &resid, rr, 14);
             if (l + 1 < L) {
                 publish_qkv_inputs<true>(c, P, l + 1, resid, rr);
             } else {  // final RMSNorm -> fp16 x for lm_head, published as half2 words
                 float* xf = reinterpret_cast<float*>(c.S.stage);
                 if (c.ownerC) xf[c.om * 96 + c.oc] = resid * rr[c.om] * pbf(c.pb, PB_lnN, c.oc, c.pdt);
-                cta_sync();
+                csync(c, __LINE__);
                 const int pairs = c.nownC / 2;
                 uint32_t* Xt = c.X + (size_t)L * P.per_layer;
                 uint32_t* Xtc = c.Xc + (size_t)L * P.per_layer;
@@ -1283,6 +1327,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         if (tracer) tr[5] = gtime();
     }
     unsigned long long* tr = trace + (size_t)(1 + L) * kTracePoints;
+    if (tid == 0) s_site = L * 16 + 5;
     if (tracer) tr[0] = gtime();
     stage_lm_head(c, P, v_b0, v_b1, logits, s_pos, step, tr);
 }
@@ -1354,9 +1399,12 @@ size_t round4(size_t w) { return (w + 3) & ~(size_t)3; }
 void plan_smem(const Params& P, int M, int smem_limit, Geometry* g) {
     const int dbuf = (int)std::max<size_t>((size_t)2 * M * P.H * 4, (size_t)M * P.I * 4);
     const int fixed = kRedBytes + M * P.ncta * kStatW * 4 + kMaxTok * 192 * 4 + kMaxTok * 96 * 3 * 4 + 32 * 8 + 2 * kMaxTok * 8 * 2 +
-                      kMaxTiles * (int)sizeof(TileInfo) + 64 * 4 + 128 + 2 * kPBBytes;
+                      4 * (int)sizeof(StageTab) + kMaxTiles * 4 + 64 * 4 + 128 + 2 * kPBBytes;
     g->dbuf_bytes = (dbuf + 127) & ~127;
-    g->ring_bytes = ((smem_limit - 2048 - fixed - g->dbuf_bytes) / 128) * 128;
+    const int slot = 2 * P.H;  // one re-tiled 16-row tile of a K = H matrix = one fp16 lm_head row
+    int ns = (smem_limit - 2048 - fixed - g->dbuf_bytes) / slot;
+    ns = std::min(ns, kMaxSlots) & ~1;  // even: lm_head chunks are slot pairs
+    g->ring_bytes = std::max(ns, 0) * slot;
     g->smem_bytes = g->ring_bytes + g->dbuf_bytes + fixed;
 }
 
@@ -1377,10 +1425,23 @@ bool persist_supported(const onebit_decoder_config& c) {
     const int sms = num_sms();
     if (sms < 64 || (sms & 1)) return false;
     if (c.num_heads * c.max_batch > sms) return false;
-    // per-CTA tile counts must fit the plan
-    const int a_max = (3 * c.hidden_size / 32 + sms - 1) / sms * 2 + 2, d_max = ((c.intermediate_size / 16 + sms - 1) / sms + 1) * 2;
-    const int c_max = ((c.hidden_size / 32 + sms - 1) / sms) * 2;
-    if (a_max > persist::kMaxTiles + 2 || d_max > persist::kMaxTiles + 2 || c_max > 4) return false;
+    // exact per-CTA tile counts against the kernel's limits and the weight ring this batch size leaves room for
+    int dev = 0, smem_limit = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return false;
+    persist::Params P;
+    memset(&P, 0, sizeof(P));
+    P.H = c.hidden_size; P.I = c.intermediate_size; P.ncta = sms;
+    persist::Geometry g;
+    plan_smem(P, c.max_batch, smem_limit, &g);
+    const int ns = g.ring_bytes / (2 * P.H), nsD = (P.I + P.H - 1) / P.H;
+    for (int cta = 0; cta < sms; ++cta) {
+        auto tiles = [&](int nb, int per) { return (int)((long long)nb * (cta + 1) / sms - (long long)nb * cta / sms) * per; };
+        const int tA = tiles(3 * P.H / 32, 2), tC = tiles(P.H / 32, 2), tD1 = tiles(P.I / 16, 2);
+        if (tA > persist::kMaxTiles || tD1 > persist::kMaxTiles || tC * 16 > 96) return false;
+        if (tA > ns || tD1 > ns || tC > ns || tC * nsD + nsD - 1 > ns) return false;
+    }
+    if (ns < 2 * persist::kLmRows) return false;
     return true;
 }
 
@@ -1539,8 +1600,7 @@ int persist_create(PersistState** out, const onebit_decoder_config& cfg, const o
     {
         Geometry g;
         plan_smem(P, cfg.max_batch, S->smem_limit, &g);
-        const int need = 16 * row_pitch(I / 8);  // the ring must hold at least the two down_proj tiles + slack
-        if (g.ring_bytes < 4 * need) { cleanup(); return fail(ONEBIT_ERR_INVALID_ARGUMENT, "persist_create: model too wide for the shared-memory ring"); }
+        if (g.ring_bytes < 4 * H) { cleanup(); return fail(ONEBIT_ERR_INVALID_ARGUMENT, "persist_create: model too wide for the shared-memory ring"); }
     }
     ONEBIT_CUDA_TRY(cudaDeviceSynchronize());
     *out = S;

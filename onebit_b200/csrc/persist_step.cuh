@@ -36,7 +36,7 @@ constexpr int kHeadDim = 128;
 constexpr int kRedBytes = 4 * kMaxTiles * 16 * 8 * 4;  // K-split partial sums [KG<=4 | 8][tiles][16][8] int32
 constexpr uint32_t kSentD = 0x80808080u;  // digit words: a byte 0x80 (= -128) is never a valid base-255 digit
 constexpr uint32_t kSentF = 0xFFFFFFFFu;  // float words: this NaN pattern is never produced (canonicalised away)
-constexpr int kTracePoints = 32;  // per trace row (one row per layer, + step start, + lm_head)
+constexpr int kTracePoints = 192;  // per trace row (one row per layer, + step start, + lm_head)
 constexpr int kTracers = 2;       // CTA 0 and the last CTA record
 
 struct BLDev {

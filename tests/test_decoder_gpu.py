@@ -139,3 +139,54 @@ def test_long_context_crosses_the_shared_memory_kv_window(tiny):
         r = oracle.rel_l2(got[:, lo:hi], want.numpy()[:, lo:hi])
         assert r < 3e-3, (lo, hi, r)
     dec.close()
+
+
+# ---- parity at the widths the bench runs (the timed kernels must be oracle-checked at their own sizes) ----
+def _wide(model, layers, tokens, batch, pdt, **env):
+    import json, os, subprocess, sys
+    root = __import__("pathlib").Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "tests" / "wide_case.py"), model, str(layers), str(tokens), str(batch), pdt],
+                       capture_output=True, text=True, env=dict(os.environ, **env), cwd=str(root), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("path,env", [("persistent", {}), ("fused", {"ONEBIT_PERSIST": "0"}),
+                                      ("split", {"ONEBIT_PERSIST": "0", "ONEBIT_FUSED": "0"})])
+@pytest.mark.parametrize("batch", [1, 4])
+def test_llama7b_width_logits_match_the_reference_port(path, env, batch):
+    """2 layers at LLaMA-7B widths (K = 4096 / 11008, 32 heads): logits of every decode path vs oracle/ref_port.py."""
+    if path == "persistent" and batch > 2:
+        batch = 2  # the persistent step serves <= 2 sequences per replica
+    out = _wide("7b", 2, 5, batch, "f32", **env)
+    assert out["status"] == 0
+    assert out["persistent"] == (path == "persistent")
+    assert out["launches"] == {"persistent": 1, "fused": 2 * 5 + 4, "split": 2 * 9 + 4}[path], out
+    assert out["rel_l2"] < 2e-3, out
+    assert out["argmax_agree"] == 1.0, out
+
+
+@pytest.mark.parametrize("path,env", [("persistent", {}), ("fused", {"ONEBIT_PERSIST": "0"})])
+def test_llama2_13b_width_logits_match_the_reference_port(path, env):
+    """1 layer at LLaMA2-13B widths (K = 5120 / 13824, 40 heads), batch 1 and fp16 parameters."""
+    out = _wide("13b", 1, 4, 1, "f16", **env)
+    assert out["status"] == 0 and out["persistent"] == (path == "persistent")
+    assert out["rel_l2"] < 2e-3, out
+    assert out["argmax_agree"] == 1.0, out
+
+
+def test_perplexity_on_the_fixed_512_token_slice_matches_to_3_decimals(tiny, golden_dir):
+    """north_star: "perplexity on a fixed 512-token slice matches to 3 decimals". tests/golden/tiny_ppl512.npz holds the
+    slice and the number the reference's own BitLlamaForCausalLMInf gives (evaluation/lm_eval.py:99-124 formula)."""
+    config, sd, _ = tiny
+    z = np.load(golden_dir / "tiny_ppl512.npz")
+    ids = torch.from_numpy(z["input_ids"])
+    assert ids.shape == (1, 512)
+    dec = BitLlamaDecoderB200(config, sd, max_seq_len=512, max_batch=1, param_dtype=torch.float32)
+    ppl = dec.perplexity(ids)
+    assert dec.status() == 0
+    last = dec.logits[0].cpu().numpy()
+    dec.close()
+    assert abs(ppl - float(z["ppl"])) < 5e-4, (ppl, float(z["ppl"]))
+    assert round(ppl, 3) == round(float(z["ppl64"]), 3) or abs(ppl - float(z["ppl64"])) < 5e-4
+    assert oracle.rel_l2(last, z["last_logits"]) < 2e-3

@@ -69,6 +69,10 @@ def wide(config, name, layers, tokens, batch=1):
     for pd, nm in ((torch.float32, "f32"), (torch.float16, "f16")):
         dec = BitLlamaDecoderB200(config, sd, max_seq_len=64, max_batch=batch, param_dtype=pd)
         got = dec.forward_tokens(ids).cpu().numpy()
+        if dec.status() != 0:
+            tr = dec.read_trace()
+            out[f"abort_info_{nm}"] = {"cta": int(tr[0, 0, 8]), "tid": int(tr[0, 0, 9]), "site_layer": int(tr[0, 0, 10]) // 16,
+                                      "site_stage": int(tr[0, 0, 10]) % 16}
         out[f"persistent_{nm}"] = dec.persistent
         out[f"status_{nm}"] = dec.status()
         out[f"logits_rel_l2_{nm}"] = float(oracle.rel_l2(got, want.numpy()))
@@ -121,6 +125,18 @@ def timing(config, name, batch=1, steps=64, prompt_len=16):
             if who == 0:
                 o.update(embed=float(lay[0, 0] - t[0, 0]) / 1e3, lm_head=float(t[1 + L, 1] - t[1 + L, 0]) / 1e3,
                          kernel_total=float(t[1 + L, 1] - t[0, 0]) / 1e3)
+            ll = L // 2  # barrier-level trace of a middle layer: (source line, us since layer start, delta)
+            n = int((t[1 + ll, 96:160] > 0).sum())
+            t0 = int(t[1 + ll, 0])
+            seq, prev = [], t0
+            for k in range(n):
+                tk = int(t[1 + ll, 32 + k])
+                seq.append([int(t[1 + ll, 96 + k]), round((tk - t0) / 1e3, 2), round((tk - prev) / 1e3, 2)])
+                prev = tk
+            o["barriers_mid_layer"] = seq
+            o["imma_C_warps"] = [[round((int(t[1 + ll, 160 + w]) - t0) / 1e3, 2), round((int(t[1 + ll, 176 + w]) - t0) / 1e3, 2)] for w in range(16)]
+            o["imma_C_inner"] = [[round((int(t[1 + ll, 24 + 2 * w]) - t0) / 1e3, 2), round((int(t[1 + ll, 25 + 2 * w]) - t0) / 1e3, 2)] for w in range(4)]
+            o["stage_ends_mid_layer"] = [round((int(t[1 + ll, k]) - t0) / 1e3, 2) for k in range(1, 6)]
             out[f"trace_us_cta{'0' if who == 0 else 'last'}"] = o
     dec.close()
     print(json.dumps(out), flush=True)
