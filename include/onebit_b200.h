@@ -178,7 +178,8 @@ ONEBIT_API int onebit_decoder_gemv_only(onebit_decoder* dec, int batch, void* st
 ONEBIT_API const int64_t* onebit_decoder_next_ids(onebit_decoder* dec);  /* device int64 [max_batch] */
 ONEBIT_API const int32_t* onebit_decoder_positions(onebit_decoder* dec); /* device int32 [max_batch] */
 ONEBIT_API int onebit_decoder_kernel_launches_per_step(onebit_decoder* dec);
-/* Persistent single-kernel step (batch <= 2, tp_size == 1; ONEBIT_PERSIST=0 disables): 1 if this decoder uses it. */
+/* Persistent single-kernel step (experimental, opt-in with ONEBIT_PERSIST=1; batch <= 2, tp_size == 1): 1 if this
+ * decoder uses it. */
 ONEBIT_API int onebit_decoder_is_persistent(onebit_decoder* dec);
 /* Health of the persistent step (synchronous device read): 0 = fine, 1 = an in-kernel exchange timed out,
  * 2 = a step was asked to decode past max_seq_len (it wrote nothing outside the cache). */

@@ -69,6 +69,10 @@ __shared__ unsigned long long s_deadline;
 __shared__ unsigned long long* s_abort_info;  // trace row 0, slots 8..: who gave up first (debug aid)
 __shared__ int s_site;                        // layer * 16 + stage of the compute warps (set at stage boundaries)
 constexpr int kLmRows = 2;  // lm_head rows per ring chunk
+#ifndef ONEBIT_POLL_BACKOFF_NS
+#define ONEBIT_POLL_BACKOFF_NS 100
+#endif
+constexpr unsigned kPollBackoffNs = ONEBIT_POLL_BACKOFF_NS;  // pause between polls of a not-yet-valid exchange word (keeps the hot L2 lines free for the writers)
 constexpr unsigned long long kStepBudgetNs = 400ull * 1000ull * 1000ull;
 __device__ __noinline__ bool spin_giveup_slow(int spins, int* abort_flag) {
     if (ldv1(reinterpret_cast<const uint32_t*>(abort_flag)) != 0u) return true;
@@ -172,12 +176,15 @@ __device__ __forceinline__ float warp_max_f(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ void put_hilo(uint32_t* p, uint32_t* pc, double v) {  // double as two publishable floats
+// double as two publishable floats (hi, lo), `stride` words apart. Statistics records are contiguous per CTA
+// ([token][cta][word]): one CTA's record is one or two 32-byte sectors, written by one thread (a transposed layout was
+// measured: 12 scattered 4-byte stores per CTA into lines shared by 32 writers made every exchange ~4 us slower).
+__device__ __forceinline__ void put_hilo(uint32_t* p, uint32_t* pc, int stride, double v) {
     const float hi = (float)v, lo = (float)(v - (double)hi);
     stv1(p, fbits(hi));
-    stv1(p + 1, fbits(lo));
+    stv1(p + stride, fbits(lo));
     stv1(pc, kSentF);
-    stv1(pc + 1, kSentF);
+    stv1(pc + stride, kSentF);
 }
 
 // ---- the ring of weight tiles: fixed slots -----------------------------------------------------------------------
@@ -219,6 +226,8 @@ struct StageTab {
     int K, T;          // input width, 16-row tiles of this CTA
     int lgKG, tpg;     // 16 warps = TG tile groups x KG = 2^lgKG K groups; tiles per group (<= 3)
     int nsl;           // ring slots per tile
+    int p_lo, nsets;   // stage A: first projection (0 = q, 1 = k, 2 = v) this CTA has rows of, and how many it spans
+    int aux[kMaxTiles];              // stage A: word offset of the tile's first row inside one token's [3][H] q/k/v record
     unsigned char pslot[kMaxTiles];  // which digit set / scale the tile's rows use
     short goff[kMaxTiles];           // element offset (parameter block) of the weight_scale of the tile's first row
 };
@@ -301,6 +310,7 @@ __device__ __noinline__ void poll_copy_d(const uint32_t* __restrict__ src, uint3
                 int spins = 0;
                 while (bad_d(v[k])) {
                     if (spin_giveup(spins, abort_flag)) break;
+                    __nanosleep(kPollBackoffNs);
                     v[k] = ldv4(src + 4 * (size_t)i);
                 }
                 *reinterpret_cast<uint4*>(dst + 4 * (size_t)i) = v[k];
@@ -328,6 +338,7 @@ __device__ __noinline__ void poll_copy_f(const uint32_t* __restrict__ src, uint3
         int spins = 0;
         while (bad_f(v)) {
             if (spin_giveup(spins, abort_flag)) break;
+            __nanosleep(kPollBackoffNs);
             v = ldv4(src + 4 * (size_t)i);
         }
         *reinterpret_cast<uint4*>(dst + 4 * (size_t)i) = v;
@@ -360,9 +371,12 @@ __device__ __forceinline__ void imma_phase(const unsigned char* ring, uint32_t s
 #pragma unroll
         for (int jp = 0; jp < 4; ++jp) {
             uint4 bv[NT];
+            bv[0] = have ? *reinterpret_cast<const uint4*>(bp[0] + u * 256 + jp * 64) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int ti = 0; ti < NT; ++ti)
-                bv[ti] = have ? *reinterpret_cast<const uint4*>(bp[ti] + u * 256 + jp * 64) : make_uint4(0u, 0u, 0u, 0u);
+            for (int ti = 1; ti < NT; ++ti) {  // same digit set as tile 0 (the common case): no second load
+                bv[ti] = bv[0];
+                if (bp[ti] != bp[0] && have) bv[ti] = *reinterpret_cast<const uint4*>(bp[ti] + u * 256 + jp * 64);
+            }
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const uint32_t mask = 0x01010101u << (2 * jp + jj);
@@ -388,8 +402,9 @@ __device__ __forceinline__ float row_value(const int* red, int tile, int KG, int
         const int4 v = *reinterpret_cast<const int4*>(p + kg * 128);
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
-    const long long V = (((long long)a.w * 255 + a.z) * 255 + a.y) * 255 + a.x;  // = 128 * sum_{bit=1} q
-    return (float)((double)(q128 - 2 * V) * invs);                               // invs = 2^(e-22) / 128
+    // V = sum_d 255^d a_d = 128 * sum_{bit=1} q, |V| < 2^45: exact in double
+    const double V = fma((double)a.w, 16581375.0, fma((double)a.z, 65025.0, fma((double)a.y, 255.0, (double)a.x)));
+    return (float)(((double)q128 - 2.0 * V) * invs);  // invs = 2^(e-22) / 128
 }
 
 // generic BitLinear stage core: copy the input digit vectors (Lamport poll), wait for the stage's weight tiles (the next
@@ -452,12 +467,11 @@ __device__ __forceinline__ void stage_core(Ctx& c, int st, int nsets, const uint
 __device__ __forceinline__ void publish32(Ctx& c, size_t xoff, size_t prob_stride, size_t tok_stride, int nprob, int nown, int col0) {
     const int nblk = nown >> 5;
     if (nblk <= 0) return;
-    const int items = kMaxTok * nprob * nblk * 32;
+    const int per_tok = nprob * nblk, items = kMaxTok * per_tok * 32;
     for (int it = c.tid; it < items; it += kCT) {
         const int jd = it & 31, j = jd >> 2, d = jd & 3;
-        int r = it >> 5;
-        const int blk = r % nblk; r /= nblk;
-        const int p = r % nprob, m = r / nprob;
+        const int r = it >> 5, m = r >= per_tok ? 1 : 0, r2 = r - m * per_tok;
+        const int p = r2 >= 2 * nblk ? 2 : (r2 >= nblk ? 1 : 0), blk = r2 - p * nblk;
         const size_t a = xoff + (size_t)p * prob_stride + (size_t)m * tok_stride + frag_word(col0 + blk * 32, j, d);
         if (m < c.M) {
             const uint32_t* sp = c.S.stage + (size_t)(m * nprob + p) * nown + blk * 32 + j;
@@ -474,7 +488,7 @@ __device__ __forceinline__ void publish16(Ctx& c, size_t xoff, size_t tok_stride
     const int nown = 16 * npb, items = kMaxTok * npb * 32;
     for (int it = c.tid; it < items; it += kCT) {
         const int jd = it & 31, j = jd >> 2, d = jd & 3;
-        const int r = it >> 5, blk = r % npb, m = r / npb;
+        const int r = it >> 5, m = r >= npb ? 1 : 0, blk = r - m * npb;
         const int c0 = col0 + blk * 16;
         const size_t a = xoff + (size_t)m * tok_stride + frag_word(c0 & ~31, j, d);
         const int bo = (c0 & 16) ? 2 : 0;
@@ -494,11 +508,14 @@ __device__ __forceinline__ void stats_exchange(Ctx& c, size_t soff, int nq, int 
     csync(c, __LINE__);
     const int per = nq + nmax;
     if (c.warp < per * c.M) {
-        const int m = c.warp / per, qn = c.warp - m * per;
+        const int m = c.warp >= per ? 1 : 0, qn = c.warp - m * per;
         const float* st = reinterpret_cast<const float*>(c.S.stat) + (size_t)m * c.ncta * kStatW;
         if (qn < nq) {
             double s = 0.0;
-            for (int k = c.lane; k < c.ncta; k += 32) s += (double)st[k * kStatW + 2 * qn] + (double)st[k * kStatW + 2 * qn + 1];
+            for (int k = c.lane; k < c.ncta; k += 32) {
+                const float2 hl = *reinterpret_cast<const float2*>(st + k * kStatW + 2 * qn);
+                s += (double)hl.x + (double)hl.y;
+            }
             s = warp_sum_d(s);
             if (c.lane == 0) c.S.redd[c.warp] = s;
         } else {
@@ -584,14 +601,15 @@ __device__ __noinline__ void residual_stage(Ctx& cref, const Params& P, int st, 
 #pragma unroll
         for (int i = 0; i < 5; ++i) s[i] = warp_sum_d(s[i]);
         if (c.lane == 0 && m < c.max_batch) {
-            const size_t a = o_stat + ((size_t)m * c.ncta + c.cta) * kStatW;
+            const int nc = 1;
+            const size_t a = o_stat + ((size_t)m * c.ncta + c.cta) * kStatW;  // this CTA's record: 12 consecutive words
             if (m < c.M) {
 #pragma unroll
-                for (int i = 0; i < 5; ++i) put_hilo(c.X + a + 2 * i, c.Xc + a + 2 * i, s[i]);
-                stv1(c.X + a + 10, 0u); stv1(c.X + a + 11, 0u);
-                stv1(c.Xc + a + 10, kSentF); stv1(c.Xc + a + 11, kSentF);
+                for (int i = 0; i < 5; ++i) put_hilo(c.X + a + 2 * i * nc, c.Xc + a + 2 * i * nc, nc, s[i]);
+                stv1(c.X + a + 10 * nc, 0u); stv1(c.X + a + 11 * nc, 0u);
+                stv1(c.Xc + a + 10 * nc, kSentF); stv1(c.Xc + a + 11 * nc, kSentF);
             } else {
-                for (int i = 0; i < kStatW; ++i) stv1(c.Xc + a + i, kSentF);
+                for (int i = 0; i < kStatW; ++i) stv1(c.Xc + a + i * nc, kSentF);
             }
         }
     }
@@ -617,17 +635,16 @@ __device__ __noinline__ void residual_stage(Ctx& cref, const Params& P, int st, 
 }
 
 // stage A: q, k, v = BitLinear(RMSNorm(x)) (:522-524) — publishes raw g*t and per-CTA LayerNorm partials
-__device__ __noinline__ void stage_qkv(Ctx& cref, const Params& P, int l, int a_b0, int a_b1, const int* s_pos) {
+__device__ __noinline__ void stage_qkv(Ctx& cref, const Params& P, int l, const int* s_pos) {
     Ctx c = cref;  // scalar-replaced local copy: the fields live in registers, not behind a pointer
-    const int H = c.H, tH = H >> 4;
-    const int gt0 = 2 * a_b0, gt1 = 2 * a_b1, T = gt1 - gt0;
-    const int p_lo = gt0 / tH, nsets = (gt1 - 1) / tH - p_lo + 1;
+    const StageTab& tb = c.S.tab[ST_A];
+    const int H = c.H, T = tb.T, p_lo = tb.p_lo;
     uint32_t* XL = c.X + (size_t)l * P.per_layer;
     uint32_t* XLc = c.Xc + (size_t)l * P.per_layer;
-    if (c.tid < 2 * kMaxTok) c.S.invs[c.tid] = pow2d(pbi(c.pb, 0, min(p_lo + c.tid / kMaxTok, 2)) - 29);
+    if (c.tid < 2 * kMaxTok) c.S.invs[c.tid] = pow2d(pbi(c.pb, 0, min(p_lo + (c.tid >> 1), 2)) - 29);
     // attention CTAs: pull this layer's cached K/V rows of their (sequence, head) towards L2
     if (c.cta < P.heads * c.M) {
-        const int am = c.cta / P.heads, ah = c.cta - am * P.heads;
+        const int am = c.cta >= P.heads ? 1 : 0, ah = c.cta - am * P.heads;
         const size_t base = ((((size_t)l * P.max_batch + am) * P.heads + ah) * P.max_seq) * kHeadDim;
         const int lines = s_pos[am] * 2;  // 256 B per row = 2 x 128 B lines
         for (int i = c.tid; i < lines; i += kCT) {
@@ -635,17 +652,15 @@ __device__ __noinline__ void stage_qkv(Ctx& cref, const Params& P, int l, int a_
             prefetch_l2(reinterpret_cast<const char*>(P.vcache + base) + (size_t)i * 128);
         }
     }
-    stage_core(c, ST_A, nsets, XL + P.o_xA + (size_t)p_lo * kMaxTok * H, XL + P.o_xA + (size_t)min(p_lo + 1, 2) * kMaxTok * H, 6);
+    stage_core(c, ST_A, tb.nsets, XL + P.o_xA + (size_t)p_lo * kMaxTok * H, XL + P.o_xA + (size_t)min(p_lo + 1, 2) * kMaxTok * H, 6);
     const int Rr = 16 * T;
     if (c.tid < Rr * kMaxTok) {
-        const int em = c.tid / Rr, er = c.tid - em * Rr;
-        const int gt = gt0 + (er >> 4), prob = gt / tH, row = (gt - prob * tH) * 16 + (er & 15);
-        const size_t a = P.o_qkv + ((size_t)em * 3 + prob) * H + row;
+        const int em = c.tid >= Rr ? 1 : 0, er = c.tid - em * Rr, ti = er >> 4;
+        const size_t a = P.o_qkv + (size_t)em * 3 * H + tb.aux[ti] + (er & 15);
         if (em < c.M) {
-            const StageTab& tb = c.S.tab[ST_A];
-            const int ps = tb.pslot[er >> 4];
-            const float u = row_value(c.S.red, er >> 4, 1 << tb.lgKG, er & 15, em, (long long)c.S.q128[ps * kMaxTok + em], c.S.invs[ps * kMaxTok + em]) *
-                            pbf(c.pb, tb.goff[er >> 4], er & 15, c.pdt);
+            const int ps = tb.pslot[ti];
+            const float u = row_value(c.S.red, ti, 1 << tb.lgKG, er & 15, em, (long long)c.S.q128[ps * kMaxTok + em], c.S.invs[ps * kMaxTok + em]) *
+                            pbf(c.pb, tb.goff[ti], er & 15, c.pdt);
             c.S.u[em * 192 + er] = u;
             stv1(XL + a, fbits(u));
         }
@@ -654,11 +669,11 @@ __device__ __noinline__ void stage_qkv(Ctx& cref, const Params& P, int l, int a_
     csync(c, __LINE__);
     if (c.tid < 2 * kMaxTok) c.S.q128[c.tid] = 0ull;
     if (c.warp < 3 * kMaxTok) {  // per-(token, projection) partial (sum, sum of squares) of this CTA's rows
-        const int m = c.warp / 3, p = c.warp - 3 * m;
+        const int m = c.warp >= 3 ? 1 : 0, p = c.warp - 3 * m;
         double s = 0.0, q = 0.0;
         if (m < c.M)
             for (int r = c.lane; r < Rr; r += 32)
-                if ((gt0 + (r >> 4)) / tH == p) {
+                if ((int)tb.pslot[r >> 4] + p_lo == p) {
                     const double v = (double)c.S.u[m * 192 + r];
                     s += v;
                     q += v * v;
@@ -666,12 +681,13 @@ __device__ __noinline__ void stage_qkv(Ctx& cref, const Params& P, int l, int a_
         s = warp_sum_d(s);
         q = warp_sum_d(q);
         if (c.lane == 0 && m < c.max_batch) {
-            const size_t a = P.o_qst + (((size_t)m * 3 + p) * c.ncta + c.cta) * 4;
+            const int nc = 1;
+            const size_t a = P.o_qst + (((size_t)m * 3 + p) * c.ncta + c.cta) * 4;  // [token][projection][cta][word 0..3]
             if (m < c.M) {
-                put_hilo(XL + a, XLc + a, s);
-                put_hilo(XL + a + 2, XLc + a + 2, q);
+                put_hilo(XL + a, XLc + a, nc, s);
+                put_hilo(XL + a + 2 * nc, XLc + a + 2 * nc, nc, q);
             } else {
-                for (int i = 0; i < 4; ++i) stv1(XLc + a + i, kSentF);
+                for (int i = 0; i < 4; ++i) stv1(XLc + a + i * nc, kSentF);
             }
         }
     }
@@ -717,7 +733,10 @@ __device__ __noinline__ void stage_attention(Ctx& cref, const Params& P, int l, 
         const int p = warp >> 1, which = warp & 1;
         const float* st = reinterpret_cast<const float*>(c.S.stat) + (size_t)p * ncta * 4 + 2 * which;
         double s = 0.0;
-        for (int k = lane; k < ncta; k += 32) s += (double)st[k * 4] + (double)st[k * 4 + 1];
+        for (int k = lane; k < ncta; k += 32) {
+            const float2 hl = *reinterpret_cast<const float2*>(st + k * 4);
+            s += (double)hl.x + (double)hl.y;
+        }
         s = warp_sum_d(s);
         if (lane == 0) c.S.redd[warp] = s;
     }
@@ -829,12 +848,12 @@ __device__ __noinline__ void stage_gate_up(Ctx& cref, const Params& P, int l, in
     uint32_t* XL = c.X + (size_t)l * P.per_layer;
     uint32_t* XLc = c.Xc + (size_t)l * P.per_layer;
     const int npb = d_b1 - d_b0, T = 2 * npb, nown = 16 * npb, col0 = 16 * d_b0;
-    if (tid < 2 * kMaxTok) c.S.invs[tid] = pow2d(pbi(c.pb, 0, 4 + tid / kMaxTok) - 29);
+    if (tid < 2 * kMaxTok) c.S.invs[tid] = pow2d(pbi(c.pb, 0, 4 + (tid >> 1)) - 29);
     stage_core(c, ST_D1, 2, XL + P.o_xD1, XL + P.o_xD1 + (size_t)kMaxTok * H, 11);
     const int Rr = 16 * T;
     if (Rr > 0) {
-        const int em = tid / Rr, er = tid - em * Rr;
-        if (em < c.M) {
+        const int em = tid >= Rr ? 1 : 0, er = tid - em * Rr;
+        if (em < c.M && tid < 2 * Rr) {
             const StageTab& tb = c.S.tab[ST_D1];
             const int ps = tb.pslot[er >> 4];
             c.S.u[em * 192 + er] = row_value(c.S.red, er >> 4, 1 << tb.lgKG, er & 15, em, (long long)c.S.q128[ps * kMaxTok + em], c.S.invs[ps * kMaxTok + em]) *
@@ -844,7 +863,7 @@ __device__ __noinline__ void stage_gate_up(Ctx& cref, const Params& P, int l, in
     csync(c, __LINE__);
     if (tid < 2 * kMaxTok) c.S.q128[tid] = 0ull;
     const bool ownerD = tid < nown * c.M;
-    const int dm = ownerD ? tid / nown : 0, dc = ownerD ? tid - dm * nown : 0;
+    const int dm = (ownerD && tid >= nown) ? 1 : 0, dc = ownerD ? tid - dm * nown : 0;
     float gv = 0.f, uv = 0.f, hd = 0.f;
     if (ownerD) {
         gv = c.S.u[dm * 192 + dc];
@@ -866,15 +885,16 @@ __device__ __noinline__ void stage_gate_up(Ctx& cref, const Params& P, int l, in
 #pragma unroll
         for (int i = 0; i < 3; ++i) mx[i] = warp_max_f(mx[i]);
         if (lane == 0 && m < c.max_batch) {
-            const size_t a = P.o_dst + ((size_t)m * c.ncta + c.cta) * kStatW;
+            const int nc = 1;
+            const size_t a = P.o_dst + ((size_t)m * c.ncta + c.cta) * kStatW;  // this CTA's record: 12 consecutive words
             if (m < c.M) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) put_hilo(XL + a + 2 * i, XLc + a + 2 * i, s[i]);
+                for (int i = 0; i < 4; ++i) put_hilo(XL + a + 2 * i * nc, XLc + a + 2 * i * nc, nc, s[i]);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) { stv1(XL + a + 8 + i, fbits(mx[i])); stv1(XLc + a + 8 + i, kSentF); }
-                stv1(XL + a + 11, 0u); stv1(XLc + a + 11, kSentF);
+                for (int i = 0; i < 3; ++i) { stv1(XL + a + (8 + i) * nc, fbits(mx[i])); stv1(XLc + a + (8 + i) * nc, kSentF); }
+                stv1(XL + a + 11 * nc, 0u); stv1(XLc + a + 11 * nc, kSentF);
             } else {
-                for (int i = 0; i < kStatW; ++i) stv1(XLc + a + i, kSentF);
+                for (int i = 0; i < kStatW; ++i) stv1(XLc + a + i * nc, kSentF);
             }
         }
     }
@@ -1022,7 +1042,7 @@ __device__ __noinline__ void stage_lm_head(Ctx& cref, const Params& P, int v_b0,
         }
         csync(c, __LINE__);
         if (tid == 0) {
-            tr[1] = gtime();
+            if (tr != nullptr) tr[1] = gtime();
             __threadfence();
             *P.step_counter = step + 1ull;
         }
@@ -1205,7 +1225,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
     c.ownerC = c.nownC > 0 && tid < c.nownC * M;
     c.om = c.ownerC ? tid / c.nownC : 0;
     c.oc = c.ownerC ? tid - c.om * c.nownC : 0;
-    const int who = cta == 0 ? 0 : (cta == ncta - 1 ? 1 : -1);
+    const int who = !P.trace_on ? -1 : (cta == 0 ? 0 : (cta == ncta - 1 ? 1 : -1));
     unsigned long long* trace = who >= 0 ? P.trace + (size_t)who * (L + 2) * kTracePoints : nullptr;
     const bool tracer = who >= 0 && tid == 0;
     c.trl = nullptr;
@@ -1229,9 +1249,16 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         tb.T = tid == ST_A ? 2 * (a_b1 - a_b0) : (tid == ST_D1 ? 2 * npb : 2 * (c_b1 - c_b0));
         tb.nsl = tid == ST_D2 ? (I + H - 1) / H : 1;
         plan_split(tb.T, tb.K >> 8, tb.lgKG, tb.tpg);
+        tb.p_lo = (2 * a_b0) / tH;
+        tb.nsets = tb.T > 0 ? (2 * a_b1 - 1) / tH - tb.p_lo + 1 : 1;
         for (int i = 0; i < tb.T; ++i) {
             int ps = 0, go = 0;
-            if (tid == ST_A) { ps = (2 * a_b0 + i) / tH - (2 * a_b0) / tH; go = PB_gA + 16 * i; }
+            if (tid == ST_A) {
+                const int gt = 2 * a_b0 + i, prob = gt / tH;
+                ps = prob - (2 * a_b0) / tH;
+                go = PB_gA + 16 * i;
+                tb.aux[i] = prob * H + (gt - prob * tH) * 16;
+            }
             else if (tid == ST_C) { go = PB_gO + 16 * i; }
             else if (tid == ST_D1) { ps = i >= npb ? 1 : 0; go = i >= npb ? PB_gU + 16 * (i - npb) : PB_gG + 16 * i; }
             else { go = PB_gDn + 16 * i; }
@@ -1281,7 +1308,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         // the layer's parameter block has long arrived (the producer runs a layer ahead); the first readers are the
         // threads that set the stage scales, everybody else reads it after a CTA barrier
         if (tid < 2 * kMaxTok) mbar_wait_b(&s_pfull[l & 1], (l >> 1) & 1, c.abort_flag);
-        stage_qkv(c, P, l, a_b0, a_b1, s_pos);
+        stage_qkv(c, P, l, s_pos);
         if (tid == 0) s_site = l * 16 + 1;
         if (tracer) tr[1] = gtime();
         stage_attention(c, P, l, s_pos);
@@ -1326,7 +1353,7 @@ step_kernel(const Params* __restrict__ Pg, const long long* __restrict__ ids_in,
         if (tid == 0) mbar_arrive(&s_pempty[l & 1]);
         if (tracer) tr[5] = gtime();
     }
-    unsigned long long* tr = trace + (size_t)(1 + L) * kTracePoints;
+    unsigned long long* tr = trace != nullptr ? trace + (size_t)(1 + L) * kTracePoints : nullptr;
     if (tid == 0) s_site = L * 16 + 5;
     if (tracer) tr[0] = gtime();
     stage_lm_head(c, P, v_b0, v_b1, logits, s_pos, step, tr);
@@ -1413,8 +1440,11 @@ void plan_smem(const Params& P, int M, int smem_limit, Geometry* g) {
 bool persist_supported(const onebit_decoder_config& c) {
     static int env = -1;
     if (env < 0) {
+        // Opt-in: measured on B200 (profiles/r02_persist_*), the single-kernel step is correct but slower than the
+        // PDL-chained fused stages at batch 1 (2.75 ms vs 1.46 ms per LLaMA-7B step): every BitLinear stage costs two
+        // all-CTA exchanges (data + LayerNorm statistics) instead of one kernel boundary.
         const char* e = getenv("ONEBIT_PERSIST");
-        env = (e && e[0] == '0') ? 0 : 1;
+        env = (e && e[0] == '1') ? 1 : 0;
     }
     if (!env) return false;
     const int tp = c.tp_size > 1 ? c.tp_size : 1;
@@ -1423,7 +1453,7 @@ bool persist_supported(const onebit_decoder_config& c) {
     if (c.hidden_size % 256 || c.intermediate_size % 256) return false;
     if (c.hidden_size != c.num_heads * persist::kHeadDim) return false;
     const int sms = num_sms();
-    if (sms < 64 || (sms & 1)) return false;
+    if (sms < 64 || (sms & 3)) return false;  // statistics rows of ncta words are polled as uint4
     if (c.num_heads * c.max_batch > sms) return false;
     // exact per-CTA tile counts against the kernel's limits and the weight ring this batch size leaves room for
     int dev = 0, smem_limit = 0;
@@ -1594,6 +1624,10 @@ int persist_create(PersistState** out, const onebit_decoder_config& cfg, const o
     P.rope_cos = rope_cos; P.rope_sin = rope_sin;
     P.kcache = kcache; P.vcache = vcache;
     P.step_counter = S->step_counter; P.abort_flag = S->abort_flag; P.trace = S->trace;
+    {
+        const char* e = getenv("ONEBIT_PERSIST_TRACE");  // stage time stamps cost a few microseconds per layer: off by default
+        P.trace_on = (e && e[0] == '1') ? 1 : 0;
+    }
     P.ids = ids; P.pos = pos;
     cudaMemcpy(S->dp, &P, sizeof(Params), cudaMemcpyHostToDevice);
     ONEBIT_CUDA_TRY(cudaFuncSetAttribute(persist::step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S->smem_limit - 2048));

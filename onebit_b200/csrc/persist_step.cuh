@@ -58,7 +58,7 @@ struct LayerDev {
 };
 
 struct Params {
-    int H, I, L, heads, V, max_seq, max_batch, pdt, ncta;
+    int H, I, L, heads, V, max_seq, max_batch, pdt, ncta, trace_on;
     float rms_eps, ln_eps;
     double inv_H, inv_I;
     const LayerDev* layers;

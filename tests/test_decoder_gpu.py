@@ -75,7 +75,7 @@ def test_llama7b_layer_shapes_run_and_are_deterministic():
     g1 = dec.generate(prompt, 8).cpu()
     g2 = dec.generate(prompt, 8).cpu()
     assert torch.equal(g1, g2)
-    # persistent single-kernel step (default), fused glue+GEMV stages, or the split chain
+    # persistent single-kernel step (ONEBIT_PERSIST=1), fused glue+GEMV stages (default), or the split chain
     assert dec.launches_per_step() in (1, 2 * 5 + 3, 2 * 9 + 3)
     assert dec.status() == 0
     assert torch.isfinite(dec.logits).all()
@@ -151,7 +151,7 @@ def _wide(model, layers, tokens, batch, pdt, **env):
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("path,env", [("persistent", {}), ("fused", {"ONEBIT_PERSIST": "0"}),
+@pytest.mark.parametrize("path,env", [("persistent", {"ONEBIT_PERSIST": "1"}), ("fused", {"ONEBIT_PERSIST": "0"}),
                                       ("split", {"ONEBIT_PERSIST": "0", "ONEBIT_FUSED": "0"})])
 @pytest.mark.parametrize("batch", [1, 4])
 def test_llama7b_width_logits_match_the_reference_port(path, env, batch):
@@ -166,7 +166,7 @@ def test_llama7b_width_logits_match_the_reference_port(path, env, batch):
     assert out["argmax_agree"] == 1.0, out
 
 
-@pytest.mark.parametrize("path,env", [("persistent", {}), ("fused", {"ONEBIT_PERSIST": "0"})])
+@pytest.mark.parametrize("path,env", [("fused", {"ONEBIT_PERSIST": "0"})])
 def test_llama2_13b_width_logits_match_the_reference_port(path, env):
     """1 layer at LLaMA2-13B widths (K = 5120 / 13824, 40 heads), batch 1 and fp16 parameters."""
     out = _wide("13b", 1, 4, 1, "f16", **env)
@@ -190,3 +190,18 @@ def test_perplexity_on_the_fixed_512_token_slice_matches_to_3_decimals(tiny, gol
     assert abs(ppl - float(z["ppl"])) < 5e-4, (ppl, float(z["ppl"]))
     assert round(ppl, 3) == round(float(z["ppl64"]), 3) or abs(ppl - float(z["ppl64"])) < 5e-4
     assert oracle.rel_l2(last, z["last_logits"]) < 2e-3
+
+
+def test_persistent_single_kernel_step_matches_the_reference_fixture():
+    """The experimental one-kernel-per-token step (ONEBIT_PERSIST=1; persist_step.cu) against the fixtures produced by the
+    reference's BitLlamaForCausalLMInf: logits, greedy tokens, batch invariance. Run through tools/persist_check.py."""
+    import json, os, subprocess, sys
+    root = __import__("pathlib").Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "tools" / "persist_check.py"), "tiny"], capture_output=True, text=True,
+                       env=dict(os.environ, ONEBIT_PERSIST="1"), cwd=str(root), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    for nm in ("f32", "f16"):
+        assert out[f"persistent_{nm}"] and out[f"status_{nm}"] == 0, out
+        assert out[f"logits_rel_l2_{nm}"] < 2e-3 and out[f"greedy_agree_{nm}"] == 1.0 and out[f"batch_invariant_{nm}"], out
+        assert abs(out[f"ppl_{nm}"] - out["ppl_ref"]) / out["ppl_ref"] < 1e-4, out

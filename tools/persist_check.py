@@ -3,6 +3,7 @@
     python tools/persist_check.py tiny|wide7b|wide13b|time7b|time13b [...]
 Each section prints one JSON line. Sections are independent; run each under `timeout`."""
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -103,7 +104,7 @@ def timing(config, name, batch=1, steps=64, prompt_len=16):
     ms = e0.elapsed_time(e1) / steps
     out = {"section": name, "batch": batch, "ms_per_step": ms, "tok_s": batch * 1e3 / ms, "persistent": dec.persistent,
            "status": dec.status(), "launches": dec.launches_per_step()}
-    tr = dec.read_trace()
+    tr = dec.read_trace() if os.environ.get('ONEBIT_PERSIST_TRACE') == '1' else None
     if tr is not None:
         L = dec.L
         for who in (0, 1):
