@@ -84,6 +84,22 @@ bool prefill_tc5_supported(int64_t m, int64_t k, int64_t n);
 size_t prefill_tc5_workspace_bytes(int64_t m, int64_t k, int act_dtype, int param_dtype);
 int launch_prefill_tc5(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m, int64_t k,
                        int64_t n, int act_dtype, int param_dtype, bool scale_by_g, void* workspace, cudaStream_t s);
+// tcgen05 path shared with the decoder: projections over the same fp16 activations, optional split-K (decode batches)
+struct Tc5LaunchProblem {
+    const int8_t* w;    // [N][K/8]
+    const __half* h16;  // [K] input_factor as fp16
+    const void* g;      // [N] weight_scale (param dtype) or nullptr
+    float* t;           // [ksplit][M][N]
+    int N;
+};
+struct Tc5Launch {
+    const __half* x16;  // [M][K]
+    int M, K, nprob, ksplit, param_dtype;
+    Tc5LaunchProblem p[3];
+};
+int launch_tc5(const Tc5Launch& L, cudaStream_t s);
+int launch_dense_tc5(const __half* x16, const __half* w16, float* out, int64_t m, int64_t k, int64_t n, cudaStream_t s);
+int launch_to_half(const void* src, __half* dst, int64_t n, int dtype, cudaStream_t s);
 int launch_quantize_tokens(const void* x, const void* h, uint8_t* digits, void* qmeta, int64_t m, int64_t k,
                            int act_dtype, int param_dtype, cudaStream_t s);
 

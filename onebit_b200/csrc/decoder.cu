@@ -30,6 +30,8 @@ namespace {
 using imma::QMeta;
 constexpr int kGlueThreads = 512;
 constexpr int kHeadDim = 128;
+constexpr int kMaxBatch = 64;     // sequences per replica (tcgen05 decode tile: 64 tokens)
+constexpr int kKSplitMax = 8;    // split-K of the batched-decode projections (t_* buffers hold that many partials)
 
 enum GlueMode {
     GLUE_EMBED_NORM = 0,   // resid_out = embed[ids];                x = RMSNorm(resid_out) * ln_w
@@ -486,6 +488,40 @@ __global__ void __launch_bounds__(256) reduce_stats_kernel(const float* __restri
     if (threadIdx.x == 0) *reinterpret_cast<float2*>(out + ((size_t)p * M + m) * 2) = make_float2((float)st[0], (float)st[1]);
 }
 
+// Batched decode on the tcgen05 path (M > 8): sum the split-K partial outputs of up to 3 projections in place
+// (t[0] += t[1..S-1]) and emit each token's LayerNorm (sum, sum of squares) in the "single CTA of partials" format
+// the glue / attention kernels read ([projection][M][2] floats). One CTA per (token, projection), fixed order.
+constexpr int kReduceSlices = 4;  // column slices per (token, projection): the statistics come out as 4 partial records
+struct ReduceArgs {
+    float* t[3];
+    int N[3];
+    float* stats;  // [nprob][kReduceSlices][M][2]
+    int M, S;
+};
+__global__ void __launch_bounds__(256) tc5_reduce_stats_kernel(const __grid_constant__ ReduceArgs A) {
+    __shared__ double shd[33 * 2];
+    imma::pdl_launch_dependents();
+    imma::pdl_wait();
+    const int m = blockIdx.x, p = blockIdx.y, z = blockIdx.z, N = A.N[p];
+    const int n4 = N >> 2, lo = (int)(((long long)n4 * z) / kReduceSlices), hi = (int)(((long long)n4 * (z + 1)) / kReduceSlices);
+    float* base = A.t[p] + (size_t)m * N;
+    const size_t split_stride = (size_t)A.M * N;
+    double st[2] = {0.0, 0.0};
+    for (int i4 = lo + threadIdx.x; i4 < hi; i4 += 256) {
+        float4 v = reinterpret_cast<const float4*>(base)[i4];
+        for (int zz = 1; zz < A.S; ++zz) {
+            const float4 w = reinterpret_cast<const float4*>(base + zz * split_stride)[i4];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        if (A.S > 1) reinterpret_cast<float4*>(base)[i4] = v;
+        st[0] += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+        st[1] += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    block_reduce_sum<2>(st, shd);
+    if (threadIdx.x == 0)
+        *reinterpret_cast<float2*>(A.stats + (((size_t)p * kReduceSlices + z) * A.M + m) * 2) = make_float2((float)st[0], (float)st[1]);
+}
+
 template <typename... KArgs, typename... Args>
 int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -532,6 +568,13 @@ struct onebit_decoder {
     // tensor-parallel geometry (tp = 1: Hl = Hk = H, Il = Ik = I)
     int tp = 1, Hl = 0, Hk = 0, Il = 0, Ik = 0, heads_l = 0;
     float *red_qkv = nullptr, *red_gu = nullptr;  // [nproj][max_batch][2] all-reduced (sum, sumsq)
+    // batched decode on the tcgen05 path (max_batch > 8): split-K factor the t_* buffers are sized for, fp16 copies of the
+    // input_factor vectors (the MMA A operand is fp16), fp16 activations of the widest layer, per-token statistics
+    int ksplit_max = 1;
+    std::vector<const __half*> h16;  // [L][7]: q k v o gate up down
+    __half* h16_store = nullptr;
+    __half* xI_f16 = nullptr;        // [B][I]
+    float *red_o = nullptr, *red_d = nullptr;  // [max_batch][2]
     // persistent single-kernel step (persist_step.cu): batch <= 2, no tensor parallelism
     PersistState* persist = nullptr;
     // host-side upper bound of every sequence's position (reset value + steps enqueued): a step that could write past
@@ -750,6 +793,114 @@ int run_fused_layers(onebit_decoder* D, int M, cudaStream_t s, bool with_attenti
     return ONEBIT_OK;
 }
 
+// split-K factor of a batched-decode projection launch: about four CTAs per SM, at least 4 K chunks per CTA
+int tc5_ksplit(int row_tiles, int K, int ksplit_max) {
+    const int want = (4 * num_sms() + row_tiles - 1) / row_tiles;
+    return std::max(1, std::min(std::min(want, ksplit_max), K / 64 / 4));
+}
+
+// Batched decode (5..64 sequences per replica): every BitLinear runs on the tcgen05 path (prefill_tc5.cu, decode tile
+// configuration: weights as the 128-row UMMA M operand with input_factor folded in, the M tokens as UMMA N, split-K over
+// grid.z), the glue kernels hand it fp16 activations, a reduce pass sums the K splits and emits the LayerNorm statistics.
+// Per layer: glue | q,k,v (one launch) | reduce | attention | glue | o | reduce | glue | gate,up (one launch) | reduce |
+// glue | down | reduce = 13 launches.
+int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int* cur_io) {
+    const onebit_decoder_config& C = D->cfg;
+    const int H = C.hidden_size, I = C.intermediate_size, pd = C.param_dtype, B = C.max_batch;
+    int cur = *cur_io, rc;
+    auto reduce = [&](float* t0, float* t1, float* t2, int n, int nprob, int S, float* stats) -> int {
+        ReduceArgs r = {};
+        r.t[0] = t0; r.t[1] = t1; r.t[2] = t2; r.N[0] = r.N[1] = r.N[2] = n; r.stats = stats; r.M = M; r.S = S;
+        ++*launches;
+        return launch_pdl(tc5_reduce_stats_kernel, dim3(M, nprob, kReduceSlices), dim3(256), 0, s, r);
+    };
+    for (int l = 0; l < C.num_layers; ++l) {
+        const onebit_layer_params& P = D->layers[l];
+        const __half* const* h16 = &D->h16[(size_t)l * 7];
+        // ---- glue 1: (embed | resid + LN(down of the previous layer)) -> RMSNorm -> fp16 x
+        GlueArgs g = {};
+        g.mode = l == 0 ? GLUE_EMBED_NORM : GLUE_RESID_NORM;
+        g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
+        g.t_a = D->t_d; g.stats_a = D->red_d; g.ncta_a = kReduceSlices;
+        g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1];
+        g.embed = D->embed; g.ids = D->ids; g.ln_w = P.input_layernorm; g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
+        rc = glue_launch(D, g, s); if (rc) return rc; ++*launches;
+        cur ^= 1;
+        // ---- q, k, v
+        Tc5Launch t = {};
+        t.x16 = D->x_f16; t.M = M; t.K = H; t.nprob = 3; t.param_dtype = pd;
+        t.ksplit = tc5_ksplit(3 * ((H + 127) / 128), H, D->ksplit_max);
+        const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
+        float* tq[3];
+        for (int i = 0; i < 3; ++i) {
+            tq[i] = D->t_qkv + (size_t)i * B * H * D->ksplit_max;
+            t.p[i].w = static_cast<const int8_t*>(qkv[i]->weight); t.p[i].h16 = h16[i]; t.p[i].g = qkv[i]->weight_scale;
+            t.p[i].t = tq[i]; t.p[i].N = H;
+        }
+        rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
+        rc = reduce(tq[0], tq[1], tq[2], H, 3, t.ksplit, D->red_qkv); if (rc) return rc;
+        // ---- attention
+        AttnArgs at = {};
+        at.t_q = tq[0]; at.t_k = tq[1]; at.t_v = tq[2];
+        const size_t pstride = (size_t)kReduceSlices * M * 2;  // statistics of one projection: kReduceSlices partial records
+        at.stats_q = D->red_qkv; at.stats_k = D->red_qkv + pstride; at.stats_v = D->red_qkv + 2 * pstride; at.ncta = kReduceSlices;
+        at.M = M; at.H = H; at.n_ln = H; at.out_ld = H; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len; at.pos = D->pos;
+        at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
+        const size_t layer_cache = (size_t)B * D->heads_l * C.max_seq_len * kHeadDim;
+        at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
+        // many (sequence, head) CTAs: stream the cached rows from L2 instead of staging them (several CTAs per SM)
+        at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = 0;
+        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), (size_t)std::max(C.max_seq_len, 4 * kHeadDim) * sizeof(float), s, at);
+        if (rc) return rc; ++*launches;
+        // ---- glue 2: attention output -> fp16
+        g = {};
+        g.mode = GLUE_PLAIN; g.M = M; g.K = H; g.nprob = 1; g.x_plain = D->attn_out; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
+        rc = glue_launch(D, g, s); if (rc) return rc; ++*launches;
+        // ---- o_proj
+        t = {};
+        t.x16 = D->x_f16; t.M = M; t.K = H; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, H, D->ksplit_max);
+        t.p[0].w = static_cast<const int8_t*>(P.o.weight); t.p[0].h16 = h16[3]; t.p[0].g = P.o.weight_scale; t.p[0].t = D->t_o; t.p[0].N = H;
+        rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
+        rc = reduce(D->t_o, nullptr, nullptr, H, 1, t.ksplit, D->red_o); if (rc) return rc;
+        // ---- glue 3: resid + LN(o) -> RMSNorm -> fp16 x
+        g = {};
+        g.mode = GLUE_RESID_NORM; g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
+        g.t_a = D->t_o; g.stats_a = D->red_o; g.ncta_a = kReduceSlices;
+        g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = P.post_attention_layernorm;
+        g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
+        rc = glue_launch(D, g, s); if (rc) return rc; ++*launches;
+        cur ^= 1;
+        // ---- gate, up
+        t = {};
+        t.x16 = D->x_f16; t.M = M; t.K = H; t.nprob = 2; t.param_dtype = pd;
+        t.ksplit = tc5_ksplit(2 * ((I + 127) / 128), H, D->ksplit_max);
+        const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
+        float* tg[2];
+        for (int i = 0; i < 2; ++i) {
+            tg[i] = D->t_gu + (size_t)i * B * I * D->ksplit_max;
+            t.p[i].w = static_cast<const int8_t*>(gu[i]->weight); t.p[i].h16 = h16[4 + i]; t.p[i].g = gu[i]->weight_scale;
+            t.p[i].t = tg[i]; t.p[i].N = I;
+        }
+        rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
+        rc = reduce(tg[0], tg[1], nullptr, I, 2, t.ksplit, D->red_gu); if (rc) return rc;
+        // ---- glue 4: silu(LN(gate)) * LN(up) -> fp16 [M][I]
+        g = {};
+        g.mode = GLUE_SILU_MUL; g.M = M; g.K = I; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->xI_f16;
+        g.t_a = tg[0]; g.stats_a = D->red_gu; g.ncta_a = kReduceSlices;
+        g.t_b = tg[1]; g.stats_b = D->red_gu + (size_t)kReduceSlices * M * 2; g.ncta_b = kReduceSlices;
+        g.ln_eps = C.ln_eps;
+        rc = glue_launch(D, g, s); if (rc) return rc; ++*launches;
+        // ---- down_proj
+        t = {};
+        t.x16 = D->xI_f16; t.M = M; t.K = I; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, I, D->ksplit_max);
+        t.p[0].w = static_cast<const int8_t*>(P.down.weight); t.p[0].h16 = h16[6]; t.p[0].g = P.down.weight_scale; t.p[0].t = D->t_d; t.p[0].N = H;
+        rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
+        rc = reduce(D->t_d, nullptr, nullptr, H, 1, t.ksplit, D->red_d); if (rc) return rc;
+    }
+    *cur_io = cur;
+    return ONEBIT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -775,7 +926,7 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     ONEBIT_REQUIRE(H == cfg->num_heads * kHeadDim, "decoder_create: only head_dim 128 (LLaMA-7B/13B) is built");
     ONEBIT_REQUIRE(H % imma::kUnitCols == 0 && I % imma::kUnitCols == 0 && I <= 14336 && H <= 14336,
                    "decoder_create: hidden/intermediate size must be multiples of 256 and <= 14336");
-    ONEBIT_REQUIRE(B >= 1 && B <= imma::kMaxTokens, "decoder_create: the fused step serves batch 1..8 per replica");
+    ONEBIT_REQUIRE(B >= 1 && B <= kMaxBatch, "decoder_create: a replica serves batch 1..64 (1..4 on the bit-plane GEMV, 5..64 on the tcgen05 path)");
     const int tp = cfg->tp_size > 1 ? cfg->tp_size : 1;
     ONEBIT_REQUIRE(cfg->num_heads % tp == 0 && I % tp == 0 && (I / tp) % 8 == 0,
                    "decoder_create: heads and intermediate size must divide by tp_size");
@@ -805,9 +956,12 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const bool big = B > 4 && tp == 1;  // batches the bit-plane GEMV cannot hold: tcgen05 path with split-K partials
+    const size_t ks = big ? kKSplitMax : 1;
+    D->ksplit_max = (int)ks;
     const size_t o_res0 = take((size_t)B * H * 4), o_res1 = take((size_t)B * H * 4);
-    const size_t o_tqkv = take((size_t)3 * B * H * 4), o_to = take((size_t)B * H * 4);
-    const size_t o_tgu = take((size_t)2 * B * I * 4), o_td = take((size_t)B * H * 4);
+    const size_t o_tqkv = take((size_t)3 * B * H * 4 * ks), o_to = take((size_t)B * H * 4 * ks);
+    const size_t o_tgu = take((size_t)2 * B * I * 4 * ks), o_td = take((size_t)B * H * 4 * ks);
     const size_t o_att = take((size_t)B * H * 4), o_log = take((size_t)B * cfg->vocab_size * 4);
     const size_t o_sqkv = take((size_t)3 * cH * B * 8), o_so = take((size_t)cH * B * 8);
     const size_t o_sgu = take((size_t)2 * cI * B * 8), o_sd = take((size_t)cH * B * 8);
@@ -818,7 +972,11 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     const size_t cache_elems = (size_t)L * B * D->heads_l * cfg->max_seq_len * kHeadDim;
     const size_t o_kc = take(cache_elems * 2), o_vc = take(cache_elems * 2);
     const size_t o_x16 = take((size_t)B * H * 2), o_ids = take(B * 8), o_ids2 = take(B * 8), o_pos = take(B * 4);
-    const size_t o_rq = take((size_t)3 * B * 2 * 4), o_rg = take((size_t)2 * B * 2 * 4);
+    const size_t o_rq = take((size_t)3 * kReduceSlices * B * 2 * 4), o_rg = take((size_t)2 * kReduceSlices * B * 2 * 4);
+    const size_t o_ro = take((size_t)kReduceSlices * B * 2 * 4), o_rd = take((size_t)kReduceSlices * B * 2 * 4);
+    const size_t o_xI = take(big ? (size_t)B * I * 2 : 16);
+    const bool need_h16 = big && cfg->param_dtype != ONEBIT_F16;
+    const size_t o_h16 = take(need_h16 ? (size_t)L * (6 * (size_t)H + I) * 2 : 16);
     cudaError_t e = cudaMalloc(&D->arena, off);
     if (e != cudaSuccess) {
         delete D;
@@ -836,6 +994,28 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     D->kcache = (__half*)(a + o_kc); D->vcache = (__half*)(a + o_vc); D->x_f16 = (__half*)(a + o_x16);
     D->ids = (long long*)(a + o_ids); D->ids_stage = (long long*)(a + o_ids2); D->pos = (int*)(a + o_pos);
     D->red_qkv = (float*)(a + o_rq); D->red_gu = (float*)(a + o_rg);
+    D->red_o = (float*)(a + o_ro); D->red_d = (float*)(a + o_rd);
+    D->xI_f16 = (__half*)(a + o_xI);
+    D->h16_store = (__half*)(a + o_h16);
+    if (big) {  // the tcgen05 A operand folds input_factor in as fp16: one-time copies when the parameters are bf16 / fp32
+        D->h16.resize((size_t)L * 7);
+        __half* hp = D->h16_store;
+        for (int l = 0; l < L; ++l) {
+            const onebit_bitlinear_params* bl[7] = {&layers[l].q, &layers[l].k, &layers[l].v, &layers[l].o, &layers[l].gate, &layers[l].up, &layers[l].down};
+            for (int i = 0; i < 7; ++i) {
+                const int k = i == 6 ? I : H;
+                if (need_h16) {
+                    const int rc = launch_to_half(bl[i]->input_factor, hp, k, cfg->param_dtype, nullptr);
+                    if (rc != ONEBIT_OK) { onebit_decoder_destroy(D); return rc; }
+                    D->h16[(size_t)l * 7 + i] = hp;
+                    hp += k;
+                } else {
+                    D->h16[(size_t)l * 7 + i] = static_cast<const __half*>(bl[i]->input_factor);
+                }
+            }
+        }
+        if (cudaDeviceSynchronize() != cudaSuccess) { onebit_decoder_destroy(D); return fail(ONEBIT_ERR_CUDA, "decoder_create: fp16 input_factor copies failed"); }
+    }
     if (persist_supported(*cfg)) {
         const int rc = persist_create(&D->persist, *cfg, layers, embed_tokens_f16, final_norm, lm_head_f16, rope_cos, rope_sin,
                                       D->kcache, D->vcache, D->ids, D->pos);
@@ -900,23 +1080,32 @@ static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced
     const size_t dgH = (size_t)C.max_batch * uH * imma::kUnitBytes;
     int rc, launches = 0;
     if (forced_ids_dev) {
-        rc = launch_pdl(copy_ids_kernel, dim3(1), dim3(32), 0, s, reinterpret_cast<const long long*>(forced_ids_dev),
+        rc = launch_pdl(copy_ids_kernel, dim3(1), dim3(kMaxBatch), 0, s, reinterpret_cast<const long long*>(forced_ids_dev),
                         D->ids, M);
         if (rc) return rc;
         ++launches;
     }
-    {   // the stand-alone GEMV keeps every token's digits of the widest layer in shared memory
-        const int nt = M <= 2 ? 1 : (M <= 4 ? 2 : 4);
-        if (imma::gemv_smem_bytes(M, std::max(uH, uI), nt) > 224 * 1024)
-            return fail(ONEBIT_ERR_INVALID_ARGUMENT,
-                        "decoder_step: batch " + std::to_string(M) + " does not fit the decode GEMV for this model width "
-                        "(LLaMA-7B: up to 4, LLaMA2-13B: up to 3 sequences per replica; use more replicas)");
-    }
+    // batches the bit-plane GEMV cannot hold (it keeps every token's digits of the widest layer in shared memory) run
+    // on the tcgen05 path when the decoder was created for them (max_batch > 4)
+    const int nt_gemv = M <= 2 ? 1 : (M <= 4 ? 2 : 4);
+    const bool gemv_fits = M <= imma::kMaxTokens && imma::gemv_smem_bytes(M, std::max(uH, uI), nt_gemv) <= 224 * 1024;
+    const bool use_tc5 = D->ksplit_max > 1 && (M > 4 || !gemv_fits);
+    if (!use_tc5 && !gemv_fits)
+        return fail(ONEBIT_ERR_INVALID_ARGUMENT,
+                    "decoder_step: batch " + std::to_string(M) + " does not fit the decode GEMV for this model width "
+                    "(LLaMA-7B: up to 4, LLaMA2-13B: up to 3 sequences); create the decoder with max_batch > 4 for the "
+                    "batched tcgen05 path");
     int cur = 0;  // residual ping-pong index holding the current stream
     int nc_d = cH;  // CTAs that wrote the (sum, sumsq) partials of the last down_proj
     bool use_fused = false;
-    rc = run_fused_layers(D, M, s, /*with_attention=*/true, /*first_is_embed=*/true, &launches, &cur, &nc_d, &use_fused);
-    if (rc) return rc;
+    if (use_tc5) {
+        rc = run_tc5_layers(D, M, s, &launches, &cur);
+        if (rc) return rc;
+        use_fused = true;  // (skips the split-chain loop below)
+    } else {
+        rc = run_fused_layers(D, M, s, /*with_attention=*/true, /*first_is_embed=*/true, &launches, &cur, &nc_d, &use_fused);
+        if (rc) return rc;
+    }
     if (!use_fused && D->tp > 1)
         return fail(ONEBIT_ERR_INVALID_ARGUMENT, "tensor-parallel decode needs the fused stages (batch <= 2, ONEBIT_FUSED != 0)");
     for (int l = 0; !use_fused && l < C.num_layers; ++l) {
@@ -1007,12 +1196,15 @@ static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced
     // ---- final: resid + LN(down) -> RMSNorm(final) -> fp16 x -> lm_head -> argmax
     GlueArgs g = {};
     g.mode = GLUE_RESID_NORM; g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1;
-    g.t_a = D->t_d; g.stats_a = D->st_d; g.ncta_a = use_fused ? nc_d : cH; g.stats_from_data = D->tp > 1;
+    g.t_a = D->t_d; g.stats_a = use_tc5 ? D->red_d : D->st_d; g.ncta_a = use_tc5 ? kReduceSlices : (use_fused ? nc_d : cH);
+    g.stats_from_data = D->tp > 1;
     g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = D->final_norm;
     g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps; g.x_f16 = D->x_f16;
     rc = glue_launch(D, g, s); if (rc) return rc; ++launches;
     float* logits = logits_dev ? logits_dev : D->logits;
-    if (M <= 2) {
+    if (M > 8) {  // dense fp16 GEMM on the tcgen05 pipeline (the GEMV form would re-read x from shared memory per row)
+        rc = launch_dense_tc5(D->x_f16, D->lm_head, logits, M, H, C.vocab_size, s);
+    } else if (M <= 2) {
         rc = launch_pdl(lm_head_kernel<2>, dim3((C.vocab_size + 7) / 8), dim3(256), (size_t)M * H * 2, s, D->lm_head,
                         (const __half*)D->x_f16, logits, C.vocab_size, H, M);
     } else {

@@ -24,14 +24,24 @@
 namespace onebit {
 namespace {
 
-constexpr int kTileN = 256;     // weight rows per CTA (two UMMA M=128 tiles)
-constexpr int kTileM = 256;     // tokens per CTA (UMMA N)
+// Two tile configurations of the same kernel:
+//   prefill   HALVES = 2 (256 weight rows per CTA), TM = 256 tokens, 3 stages  — one expanded tile serves 256 tokens;
+//   decode    HALVES = 1 (128 weight rows per CTA), TM = 64 tokens, 2 stages, optional split-K over grid.z — batches of
+//             5..64 sequences: many small CTAs (4 per SM, 53 KB each) so that all 148 SMs stream and expand weights.
+// DENSE = true replaces the sign expanders by a second TMA stream of a dense fp16 matrix (lm_head for those batches).
 constexpr int kChunkK = 64;     // K columns per pipeline stage (= one 128-byte swizzle row of fp16)
-constexpr int kStages = 3;
 constexpr int kThreads = 192;
-constexpr int kABytes = kTileN * kChunkK * 2;  // 32 KB
-constexpr int kBBytes = kTileM * kChunkK * 2;  // 32 KB
-constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024;  // + alignment slack
+constexpr int kMaxProblems = 3; // projections that share the activation tile in one launch (q/k/v, gate/up)
+template <int HALVES, int TM>
+struct Tile {
+    static constexpr int kTileN = HALVES * 128;
+    static constexpr int kStages = HALVES == 2 ? 3 : 2;  // decode: shallow pipeline, 4 CTAs per SM instead
+    static constexpr int kHStage = HALVES == 2 ? 1 : 256;  // uint4 slots of shared memory for the CTA's slice of input_factor (decode)
+    static constexpr int kABytes = kTileN * kChunkK * 2;
+    static constexpr int kBBytes = TM * kChunkK * 2;
+    static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024;  // + alignment slack
+    static constexpr int kTmemCols = HALVES * TM < 32 ? 32 : HALVES * TM;       // power of two for these configurations
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -84,33 +94,55 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ uint2 ldg_nc_u2(const uint8_t* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+struct Tc5Problem {
+    const uint8_t* w;   // [N][K/8] packed signs (unused by the DENSE variant)
+    const __half* h;    // [K] fp16 input_factor
+    const void* g;      // [N] TP weight_scale or nullptr
+    float* t;           // [ksplit][M][N] fp32 (split z writes its partial sums at t + z * M * N)
+    int N, tile_begin;  // rows; first row tile (blockIdx.x) of this problem
+};
 struct PrefillArgs {
-    const uint8_t* w;   // [N][K/8]
-    const __half* h;    // [K] fp16
-    const void* g;      // [N] TP or nullptr
-    float* t;           // [M][N] fp32
-    int M, N, K;
+    Tc5Problem p[kMaxProblems];
+    int nprob, M, K, ksplit;
 };
 
-template <typename TP>
+template <typename TP, int HALVES, int TM, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1)
-prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ PrefillArgs A) {
+prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap amap,
+                   const __grid_constant__ PrefillArgs A) {
+    using TL = Tile<HALVES, TM>;
+    constexpr int kTileN = TL::kTileN, kTileM = TM, kStages = TL::kStages, kABytes = TL::kABytes, kBBytes = TL::kBBytes;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sA = smem;                          // [stage][256 rows][128 B] swizzled
-    unsigned char* sB = smem + kStages * kABytes;      // [stage][256 rows][128 B] swizzled (TMA)
+    unsigned char* sA = smem;                          // [stage][HALVES * 128 rows][128 B] swizzled
+    unsigned char* sB = smem + kStages * kABytes;      // [stage][TM rows][128 B] swizzled (TMA)
     __shared__ __align__(8) uint64_t full_a[kStages], full_b[kStages], empty[kStages], tmem_full;
     __shared__ uint32_t tmem_base_s;
+    __shared__ uint4 h_stage[TL::kHStage];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * kTileN, m0 = blockIdx.y * kTileM;
-    const int nchunks = A.K / kChunkK;
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxProblems; ++i)
+        if (i < A.nprob && (int)blockIdx.x >= A.p[i].tile_begin) pi = i;
+    const Tc5Problem& P = A.p[pi];
+    const int n0 = ((int)blockIdx.x - P.tile_begin) * kTileN, m0 = blockIdx.y * kTileM;
+    const int nchunks_all = A.K / kChunkK;
+    const int c_begin = (int)(((long long)nchunks_all * blockIdx.z) / A.ksplit);
+    const int nchunks = (int)(((long long)nchunks_all * (blockIdx.z + 1)) / A.ksplit) - c_begin;  // this CTA's K slice
+    float* tout = P.t + (size_t)blockIdx.z * A.M * P.N;
     const int m_valid = min(kTileM, A.M - m0);
     const int umma_n = max(16, (m_valid + 15) & ~15);  // tokens covered by the MMA (multiple of 16)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_a[s], 128);
+            mbar_init(&full_a[s], DENSE ? 1 : 128);
             mbar_init(&full_b[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -118,8 +150,8 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
     }
-    if (warp == 1) {  // TMEM: 512 columns (two 128 x 256 fp32 accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    if (warp == 1) {  // TMEM: HALVES accumulators of 128 lanes x TM fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TL::kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -134,7 +166,11 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                 const int s = c % kStages, it = c / kStages;
                 if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
                 mbar_expect_tx(&full_b[s], kBBytes);
-                tma_load_2d(sB + s * kBBytes, &xmap, c * kChunkK, m0, &full_b[s]);
+                tma_load_2d(sB + s * kBBytes, &xmap, (c_begin + c) * kChunkK, m0, &full_b[s]);
+                if (DENSE) {  // the A tile is a plain fp16 matrix: second TMA stream, same 128B-swizzled layout
+                    mbar_expect_tx(&full_a[s], kABytes);
+                    tma_load_2d(sA + s * kABytes, &amap, (c_begin + c) * kChunkK, n0, &full_a[s]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -148,12 +184,12 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(sA + s * kABytes), b_addr = smem_u32(sB + s * kBBytes);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < HALVES; ++half) {
 #pragma unroll
                     for (int k = 0; k < kChunkK / 16; ++k) {
                         const uint64_t ad = umma_desc_sw128(a_addr + half * (128 * 128) + k * 32);
                         const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
-                        umma_f16(tmem_base + half * 256, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                        umma_f16(tmem_base + half * TM, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
@@ -164,23 +200,51 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         // ===== sign expanders: thread e (0..127) owns rows e and e + 128 of the CTA's weight tile =====
         const int e = threadIdx.x - 64;
         const int Kb = A.K >> 3;
-        const uint8_t* wrow0 = A.w + (size_t)min(n0 + e, A.N - 1) * Kb;
-        const uint8_t* wrow1 = A.w + (size_t)min(n0 + e + 128, A.N - 1) * Kb;
-        for (int c = 0; c < nchunks; ++c) {
+        const uint8_t* wrow0 = P.w + (size_t)min(n0 + e, P.N - 1) * Kb + (size_t)c_begin * 8;
+        const uint8_t* wrow1 = P.w + (size_t)min(n0 + e + 128, P.N - 1) * Kb + (size_t)c_begin * 8;
+        const bool h_staged = !DENSE && TL::kHStage > 1 && nchunks * 8 <= TL::kHStage;
+        if (h_staged) {  // the CTA's K slice of input_factor: one cooperative copy instead of 8 L1/L2 round trips per chunk
+            const uint4* hsrc = reinterpret_cast<const uint4*>(P.h + (size_t)c_begin * kChunkK);
+            for (int i = e; i < nchunks * 8; i += 128) h_stage[i] = __ldg(hsrc + i);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        // The 8 weight bytes of a row and chunk come straight from HBM: keep kPF chunks of them in flight in registers, so
+        // that an iteration never waits a full memory round trip (the decode configuration has no long MMA to hide it)
+        constexpr int kPF = 8;
+        uint2 q0[kPF], q1[kPF];
+#pragma unroll
+        for (int i = 0; i < kPF; ++i) {
+            q0[i] = make_uint2(0u, 0u);
+            q1[i] = make_uint2(0u, 0u);
+            if (!DENSE && i < nchunks) {
+                q0[i] = ldg_nc_u2(wrow0 + i * 8);
+                if (HALVES == 2) q1[i] = ldg_nc_u2(wrow1 + i * 8);
+            }
+        }
+        for (int cb = 0; !DENSE && cb < nchunks; cb += kPF) {
+#pragma unroll
+          for (int ci = 0; ci < kPF; ++ci) {
+            const int c = cb + ci;
+            if (c >= nchunks) break;
             const int s = c % kStages, it = c / kStages;
-            const uint2 w0 = *reinterpret_cast<const uint2*>(wrow0 + c * 8);
-            const uint2 w1 = *reinterpret_cast<const uint2*>(wrow1 + c * 8);
-            const uint4* hp = reinterpret_cast<const uint4*>(A.h + c * kChunkK);  // 8 x 16 B, same for every row
+            const uint2 w0 = q0[ci];
+            const uint2 w1 = q1[ci];
+            if (c + kPF < nchunks) {  // refill the slot with the chunk kPF ahead
+                q0[ci] = ldg_nc_u2(wrow0 + (c + kPF) * 8);
+                if (HALVES == 2) q1[ci] = ldg_nc_u2(wrow1 + (c + kPF) * 8);
+            }
+            // 8 x 16 B of input_factor, the same for every row: from the staged slice (decode) or through L1 (prefill)
+            const uint4* hp = h_staged ? h_stage + c * 8 : reinterpret_cast<const uint4*>(P.h + (size_t)(c_begin + c) * kChunkK);
             if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
             unsigned char* base = sA + s * kABytes;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < HALVES; ++half) {
                 const uint2 w = half ? w1 : w0;
                 const int r = e + half * 128;
                 unsigned char* rowp = base + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {  // 16-byte chunk q = columns 8q .. 8q+7 = byte q of the 64-bit word
-                    const uint4 hv = __ldg(hp + q);
+                    const uint4 hv = h_staged ? hp[q] : __ldg(hp + q);
                     // byte q of the row chunk: bit i = column 8q + i. An 8-bit value times (0x40008000 >> 2i) is two
                     // disjoint shifted copies (no carries): bit 2i lands on bit 15, bit 2i+1 on bit 31.
                     const uint32_t b8 = __byte_perm(q < 4 ? w.x : w.y, 0u, 0x4440u | (uint32_t)(q & 3));
@@ -194,19 +258,20 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
             mbar_arrive(&full_a[s]);
+          }
         }
         // ===== epilogue: TMEM -> registers -> * g -> t[m][n] (lanes = consecutive n: coalesced) =====
         mbar_wait(&tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < HALVES; ++half) {
             const int n = n0 + half * 128 + quarter * 32 + lane;
-            const float gs = (A.g != nullptr && n < A.N) ? to_f32(static_cast<const TP*>(A.g)[n]) : 1.f;
+            const float gs = (P.g != nullptr && n < P.N) ? to_f32(static_cast<const TP*>(P.g)[n]) : 1.f;
 #pragma unroll 1
             for (int cb = 0; cb < umma_n; cb += 32) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 256 + cb);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * TM + cb);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
@@ -217,11 +282,11 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (n < A.N) {
+                if (n < P.N) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int m = m0 + cb + j;
-                        if (m < A.M) A.t[(size_t)m * A.N + n] = __uint_as_float(v[j]) * gs;
+                        if (m < A.M) tout[(size_t)m * P.N + n] = __uint_as_float(v[j]) * gs;
                     }
                 }
             }
@@ -229,7 +294,7 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TL::kTmemCols) : "memory");
 }
 
 // x (bf16 / fp32) -> fp16 scratch, so that the TMA / MMA B operand is always fp16
@@ -255,6 +320,35 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+int encode_2d(CUtensorMap* map, const __half* base, int64_t rows, int64_t k, int box_rows) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return fail(ONEBIT_ERR_CUDA, "tcgen05 path: cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(ONEBIT_ERR_CUDA, "tcgen05 path: cuTensorMapEncodeTiled failed, code " + std::to_string((int)cr));
+    return ONEBIT_OK;
+}
+
+template <typename TP, int HALVES, int TM, bool DENSE>
+int launch_inst(const CUtensorMap& xmap, const CUtensorMap& amap, const PrefillArgs& a, dim3 grid, cudaStream_t s) {
+    auto kern = prefill_tc5_kernel<TP, HALVES, TM, DENSE>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<HALVES, TM>::kSmemBytes));
+        configured[dev] = true;
+    }
+    kern<<<grid, kThreads, Tile<HALVES, TM>::kSmemBytes, s>>>(xmap, amap, a);
+    ONEBIT_CUDA_TRY(cudaGetLastError());
+    return ONEBIT_OK;
+}
+
 }  // namespace
 
 bool prefill_tc5_supported(int64_t m, int64_t k, int64_t n) {
@@ -268,69 +362,80 @@ size_t prefill_tc5_workspace_bytes(int64_t m, int64_t k, int act_dtype, int para
     return b + 256;
 }
 
+int launch_to_half(const void* src, __half* dst, int64_t n, int dtype, cudaStream_t s) {
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (dtype == ONEBIT_BF16) to_half_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), dst, n);
+    else if (dtype == ONEBIT_F32) to_half_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(src), dst, n);
+    else return fail(ONEBIT_ERR_INVALID_ARGUMENT, "launch_to_half: source is already fp16");
+    ONEBIT_CUDA_TRY(cudaGetLastError());
+    return ONEBIT_OK;
+}
+
 int launch_prefill_tc5(const void* x, const int8_t* w, const void* g, const void* h, float* t, int64_t m, int64_t k,
                        int64_t n, int act_dtype, int param_dtype, bool scale_by_g, void* workspace, cudaStream_t s) {
     ONEBIT_REQUIRE(prefill_tc5_supported(m, k, n), "prefill_tc5: needs K % 64 == 0");
-    EncodeTiledFn encode = get_encode_fn();
-    if (!encode) return fail(ONEBIT_ERR_CUDA, "prefill_tc5: cuTensorMapEncodeTiled entry point not available");
     char* ws = static_cast<char*>(workspace);
     const __half* x16 = static_cast<const __half*>(x);
     if (act_dtype != ONEBIT_F16) {
         __half* buf = reinterpret_cast<__half*>(ws);
         ws += (((size_t)m * k * 2) + 255) & ~(size_t)255;
-        const int64_t total = m * k;
-        const unsigned grid = (unsigned)((total + 255) / 256);
-        if (act_dtype == ONEBIT_BF16)
-            to_half_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), buf, total);
-        else
-            to_half_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), buf, total);
-        ONEBIT_CUDA_TRY(cudaGetLastError());
+        const int rc = launch_to_half(x, buf, m * k, act_dtype, s);
+        if (rc) return rc;
         x16 = buf;
     }
     const __half* h16 = static_cast<const __half*>(h);
     if (param_dtype != ONEBIT_F16) {
         __half* buf = reinterpret_cast<__half*>(ws);
-        const unsigned grid = (unsigned)((k + 255) / 256);
-        if (param_dtype == ONEBIT_BF16)
-            to_half_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(h), buf, k);
-        else
-            to_half_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(h), buf, k);
-        ONEBIT_CUDA_TRY(cudaGetLastError());
+        const int rc = launch_to_half(h, buf, k, param_dtype, s);
+        if (rc) return rc;
         h16 = buf;
     }
+    Tc5Launch L = {};
+    L.x16 = x16; L.M = (int)m; L.K = (int)k; L.nprob = 1; L.ksplit = 1; L.param_dtype = param_dtype;
+    L.p[0].w = w; L.p[0].h16 = h16; L.p[0].g = scale_by_g ? g : nullptr; L.p[0].t = t; L.p[0].N = (int)n;
+    return launch_tc5(L, s);
+}
+
+// Shared launcher: `nprob` projections over the same fp16 activations [M][K]; each writes ksplit partial outputs
+// [ksplit][M][N] (ksplit = 1: the final t). M <= 64 selects the decode tile configuration.
+int launch_tc5(const Tc5Launch& L, cudaStream_t s) {
+    ONEBIT_REQUIRE(L.nprob >= 1 && L.nprob <= kMaxProblems && L.M >= 1 && L.K % kChunkK == 0 && L.ksplit >= 1 &&
+                       L.K / kChunkK >= L.ksplit, "launch_tc5: bad arguments");
+    const bool small = L.M <= 64;
+    const int tile_n = small ? 128 : 256, tile_m = small ? 64 : 256;
+    ONEBIT_REQUIRE(small || L.ksplit == 1, "launch_tc5: split-K is built for the decode tile configuration only");
     CUtensorMap xmap;
-    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)m};
-    const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)kTileM};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(x16), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return fail(ONEBIT_ERR_CUDA, "prefill_tc5: cuTensorMapEncodeTiled failed, code " + std::to_string((int)cr));
-    PrefillArgs a;
-    a.w = reinterpret_cast<const uint8_t*>(w);
-    a.h = h16;
-    a.g = scale_by_g ? g : nullptr;
-    a.t = t;
-    a.M = (int)m;
-    a.N = (int)n;
-    a.K = (int)k;
-    dim3 grid((unsigned)((n + kTileN - 1) / kTileN), (unsigned)((m + kTileM - 1) / kTileM));
+    int rc = encode_2d(&xmap, L.x16, L.M, L.K, tile_m);
+    if (rc) return rc;
+    PrefillArgs a = {};
+    a.nprob = L.nprob; a.M = L.M; a.K = L.K; a.ksplit = L.ksplit;
+    int tiles = 0;
+    for (int i = 0; i < L.nprob; ++i) {
+        a.p[i].w = reinterpret_cast<const uint8_t*>(L.p[i].w); a.p[i].h = L.p[i].h16; a.p[i].g = L.p[i].g; a.p[i].t = L.p[i].t;
+        a.p[i].N = L.p[i].N; a.p[i].tile_begin = tiles;
+        tiles += (L.p[i].N + tile_n - 1) / tile_n;
+    }
+    dim3 grid((unsigned)tiles, (unsigned)((L.M + tile_m - 1) / tile_m), (unsigned)L.ksplit);
     ONEBIT_REQUIRE(grid.y <= 65535, "prefill_tc5: M too large (max 16.7M tokens)");
-    return dispatch_dtype(param_dtype, [&](auto pt) {
+    return dispatch_dtype(L.param_dtype, [&](auto pt) {
         using TP = decltype(pt);
-        auto kern = prefill_tc5_kernel<TP>;
-        static bool configured[64] = {false};
-        int dev = 0;
-        ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && !configured[dev]) {
-            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-            configured[dev] = true;
-        }
-        kern<<<grid, kThreads, kSmemBytes, s>>>(xmap, a);
-        ONEBIT_CUDA_TRY(cudaGetLastError());
-        return ONEBIT_OK;
+        return small ? launch_inst<TP, 1, 64, false>(xmap, xmap, a, grid, s) : launch_inst<TP, 2, 256, false>(xmap, xmap, a, grid, s);
     });
+}
+
+// out[m][n] = sum_k W[n][k] * x[m][k]: dense fp16 weights through the same pipeline (lm_head for decode batches > 8)
+int launch_dense_tc5(const __half* x16, const __half* w16, float* out, int64_t m, int64_t k, int64_t n, cudaStream_t s) {
+    ONEBIT_REQUIRE(m >= 1 && m <= 64 && k % kChunkK == 0 && n >= 1, "launch_dense_tc5: needs 1 <= M <= 64, K % 64 == 0");
+    CUtensorMap xmap, amap;
+    int rc = encode_2d(&xmap, x16, m, k, 64);
+    if (rc) return rc;
+    rc = encode_2d(&amap, w16, n, k, 128);
+    if (rc) return rc;
+    PrefillArgs a = {};
+    a.nprob = 1; a.M = (int)m; a.K = (int)k; a.ksplit = 1;
+    a.p[0].t = out; a.p[0].N = (int)n; a.p[0].tile_begin = 0;
+    dim3 grid((unsigned)((n + 127) / 128), 1, 1);
+    return launch_inst<__half, 1, 64, true>(xmap, amap, a, grid, s);
 }
 
 }  // namespace onebit

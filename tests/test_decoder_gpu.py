@@ -161,7 +161,10 @@ def test_llama7b_width_logits_match_the_reference_port(path, env, batch):
     out = _wide("7b", 2, 5, batch, "f32", **env)
     assert out["status"] == 0
     assert out["persistent"] == (path == "persistent")
-    assert out["launches"] == {"persistent": 1, "fused": 2 * 5 + 4, "split": 2 * 9 + 4}[path], out
+    want = {"persistent": 1, "fused": 2 * 5 + 4, "split": 2 * 9 + 4}[path]
+    if path == "fused" and batch > 2:
+        want = 2 * 9 + 4  # batches of 3..8 sequences run the split chain (glue kernel + GEMV) at these widths
+    assert out["launches"] == want, out
     assert out["rel_l2"] < 2e-3, out
     assert out["argmax_agree"] == 1.0, out
 

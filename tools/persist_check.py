@@ -159,5 +159,9 @@ if __name__ == "__main__":
             timing(LLAMA_7B, "time7b_b2", batch=2)
         elif arg == "time13b":
             timing(LLAMA2_13B, "time13b")
+        elif arg.startswith("time7b_b"):
+            timing(LLAMA_7B, arg, batch=int(arg[len("time7b_b"):]), steps=32)
+        elif arg.startswith("time13b_b"):
+            timing(LLAMA2_13B, arg, batch=int(arg[len("time13b_b"):]), steps=32)
         else:
             raise SystemExit(f"unknown section {arg}")
