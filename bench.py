@@ -164,14 +164,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     name, cfg = model_config(args.model)
-    metric = METRIC if (args.model == "7b" and args.batch == 1) else f"{name} decode tok/s (greedy, batch {args.batch} per GPU)"
-    B, K, W = args.batch, args.steps, args.warmup
-    prompt_len = 16
-    sd = synthetic_state_dict(cfg, seed=rank)
-    dec = BitLlamaDecoderB200(cfg, sd, device=dev, max_seq_len=prompt_len + 2 * (K + W) + 32, max_batch=B)
-    del sd
-    gen = torch.Generator().manual_seed(1234 + rank)
-    prompt = torch.randint(3, cfg["vocab_size"], (B, prompt_len), generator=gen)
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        pk = json.loads(peaks_path.read_text())
+        peak, peak_src = pk["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        tpeak, tpeak_src = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        tpeak, tpeak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -184,112 +184,146 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def max_over_ranks(ms: float) -> float:
         return replicas.max_over_ranks(ms, device=dev)
 
-    def prefill():
-        dec.reset(prompt[:, 0])
-        ids = prompt.to(dev)
-        for i in range(prompt_len):
-            dec.step(ids[:, i])
+    def measure(model_name, cfg, B, K, W, sampler=None, with_e2e=True):
+        """Decode throughput of one replica per GPU at batch B: device-resident loop, end-to-end loop with host ids in and
+        out every step, and the BitLinear projection launches of a step on their own (roofline of the dominant kernel)."""
+        prompt_len = 16
+        sd = synthetic_state_dict(cfg, seed=rank)
+        dec = BitLlamaDecoderB200(cfg, sd, device=dev, max_seq_len=prompt_len + 2 * (K + W) + 32, max_batch=B)
+        del sd
+        gen = torch.Generator().manual_seed(1234 + rank)
+        prompt = torch.randint(3, cfg["vocab_size"], (B, prompt_len), generator=gen)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    # ---- device-resident decode: K timed steps
-    prefill()
-    for _ in range(max(W, 3)):
-        dec.step()
-    if sampler:
-        sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        dec.step()
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    value = world * B * K / (ms * 1e-3)
+        def prefill():
+            dec.reset(prompt[:, 0])
+            ids = prompt.to(dev)
+            for i in range(prompt_len):
+                dec.step(ids[:, i])
 
-    # ---- end to end through the public API: ids from pinned host memory in, next ids back to the host, every step
-    prefill()
-    h_in = torch.empty(B, dtype=torch.int64).pin_memory()
-    h_out = torch.empty(B, dtype=torch.int64).pin_memory()
-    h_in.copy_(dec.next_ids().cpu())
-    for _ in range(max(W, 3)):
-        dec.step(h_in)
-        h_out.copy_(dec.next_ids(), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        h_in.copy_(h_out)
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for _ in range(K):
-        dec.step(h_in)                                   # H2D of the fed ids (pinned -> device) + graph replay
-        h_out.copy_(dec.next_ids(), non_blocking=True)   # D2H of the step's result
-        torch.cuda.current_stream(dev).synchronize()
-        h_in.copy_(h_out)                                # host feeds the token back (what a serving loop does)
-    e3.record()
-    barrier()
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
-    e2e_value = world * B * K / (ms_e2e * 1e-3)
-
-    # ---- dominant kernel alone: the 4 x L BitLinear GEMV launches of a step, back to back, CUDA events
-    bb = bitlinear_bytes(cfg, B)
-    g = torch.cuda.CUDAGraph()
-    _lib.check(lib.onebit_decoder_gemv_only(dec._handle, B, torch.cuda.current_stream(dev).cuda_stream), "gemv_only")
-    torch.cuda.synchronize(dev)
-    with torch.cuda.graph(g):
+        # ---- device-resident decode: K timed steps
+        prefill()
+        for _ in range(max(W, 3)):
+            dec.step()
+        if sampler:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            dec.step()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        out = {"batch": B, "value": world * B * K / (ms * 1e-3), "ms_per_step": ms / K, "launches_per_step": dec.launches_per_step(),
+               "prompt_len": prompt_len}
+        # ---- end to end through the public API: ids from pinned host memory in, next ids back to the host, every step
+        if with_e2e:
+            prefill()
+            h_in = torch.empty(B, dtype=torch.int64).pin_memory()
+            h_out = torch.empty(B, dtype=torch.int64).pin_memory()
+            h_in.copy_(dec.next_ids().cpu())
+            for _ in range(max(W, 3)):
+                dec.step(h_in)
+                h_out.copy_(dec.next_ids(), non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                h_in.copy_(h_out)
+            barrier()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            for _ in range(K):
+                dec.step(h_in)                                   # H2D of the fed ids (pinned -> device) + graph replay
+                h_out.copy_(dec.next_ids(), non_blocking=True)   # D2H of the step's result
+                torch.cuda.current_stream(dev).synchronize()
+                h_in.copy_(h_out)                                # host feeds the token back (what a serving loop does)
+            e3.record()
+            barrier()
+            ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+            out["e2e"] = {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * B,
+                          "d2h_bytes_per_step": 8 * B, "ms_per_step": ms_e2e / K}
+        # ---- dominant kernel alone: the 4 x L BitLinear projection launches of a step, back to back, CUDA events
+        bb = bitlinear_bytes(cfg, B)
+        g = torch.cuda.CUDAGraph()
         _lib.check(lib.onebit_decoder_gemv_only(dec._handle, B, torch.cuda.current_stream(dev).cuda_stream), "gemv_only")
-    for _ in range(3):
-        g.replay()
-    barrier()
-    reps = 20
-    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e4.record()
-    for _ in range(reps):
-        g.replay()
-    e5.record()
-    barrier()
-    gemv_ms = e4.elapsed_time(e5) / reps
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(g):
+            _lib.check(lib.onebit_decoder_gemv_only(dec._handle, B, torch.cuda.current_stream(dev).cuda_stream), "gemv_only")
+        for _ in range(3):
+            g.replay()
+        barrier()
+        reps = 20 if B <= 4 else 5
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        for _ in range(reps):
+            g.replay()
+        e5.record()
+        barrier()
+        gemv_ms = e4.elapsed_time(e5) / reps
+        launches = bb["gemv_launches"]
+        bytes_per_launch = bb["per_step"] / launches
+        achieved = bytes_per_launch / (gemv_ms * 1e-3 / launches) / 1e9
+        H, I, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_hidden_layers"]
+        flops_step = 2.0 * B * L * (4 * H * H + 3 * H * I)
+        if B > 4:
+            kname = ("prefill_tc5_kernel<decode tile> (tcgen05.mma kind::f16, packed signs expanded in registers with "
+                     "input_factor folded in, TMA activations, split-K; one launch per projection group)")
+        elif os.environ.get("ONEBIT_FUSED", "1") != "0":
+            kname = "fused::fused_gemv_kernel (glue prologue + bit-plane IMMA packed-sign GEMV, one launch per BitLinear group)"
+        else:
+            kname = "imma::gemv_kernel (bit-plane IMMA packed-sign GEMV)"
+        traffic = None
+        tpath = ROOT / "profiles" / "r01_gemv_traffic.json"
+        if tpath.exists() and B <= 4:
+            traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+        out["roofline"] = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                           "bytes_per_launch": bytes_per_launch, "us_per_launch": gemv_ms * 1e3 / launches,
+                           "launches_timed": launches * reps,
+                           "how": f"CUDA events around {reps} replays of a graph holding the step's 4xL BitLinear projection "
+                                  "launches (attention / glue / lm_head left out), distinct weights per launch "
+                                  "(weight stream per replay > L2)",
+                           "tensor": {"achieved_tflops": flops_step / (gemv_ms * 1e-3) / 1e12, "peak_tflops": tpeak,
+                                      "frac": flops_step / (gemv_ms * 1e-3) / 1e12 / tpeak, "peak_source": tpeak_src},
+                           "step_level": {"bitlinear_GBs_over_whole_step": bb["per_step"] / (ms / K * 1e-3) / 1e9,
+                                          "frac": bb["per_step"] / (ms / K * 1e-3) / 1e9 / peak}}
+        dec.close()
+        del dec
+        torch.cuda.empty_cache()
+        return out
+
+    B, K, W = args.batch, args.steps, args.warmup
+    metric = METRIC if (args.model == "7b" and B == 1) else f"{name} decode tok/s (greedy, batch {B} per GPU)"
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    main_res = measure(name, cfg, B, K, W, sampler=sampler)
     clocks = sampler.stop() if sampler else None
+    # the metric's second operating point ("decode tok/s @ b=1/32"): the batched tcgen05 path, same model, same run
+    extra = {}
+    if B == 1 and os.environ.get("ONEBIT_BENCH_EXTRA", "1") != "0":
+        for label, mname, eb in (("batch32", args.model, 32),):
+            try:
+                ename, ecfg = model_config(mname)
+                r = measure(ename, ecfg, eb, min(K, 32), 3, with_e2e=True)
+                r["workload"] = f"{ename} greedy decode, batch {eb} per GPU, 16-token prompt then {min(K, 32)} generated tokens"
+                extra[label] = r
+            except Exception as exc:  # the headline line must survive a failure of the secondary operating point
+                extra[label] = {"error": str(exc)[:300]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
     if rank != 0:
         return
-    peaks_path = ROOT / "MEASURED_PEAKS.json"
-    if peaks_path.exists():
-        peak, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    launches = bb["gemv_launches"]
-    bytes_per_launch = bb["per_step"] / launches
-    achieved = bytes_per_launch / (gemv_ms * 1e-3 / launches) / 1e9
-    traffic = None
-    tpath = ROOT / "profiles" / "r01_gemv_traffic.json"
-    if tpath.exists():
-        traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
-    fused_on = os.environ.get("ONEBIT_FUSED", "1") != "0"
-    kname = ("fused::fused_gemv_kernel (glue prologue + bit-plane IMMA packed-sign GEMV, one launch per BitLinear group)"
-             if fused_on else "imma::gemv_kernel (bit-plane IMMA packed-sign GEMV)")
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": bytes_per_launch, "us_per_launch": gemv_ms * 1e3 / launches,
-                "launches_timed": launches * reps,
-                "how": "CUDA events around 20 replays of a graph holding the step's 4xL BitLinear-stage launches (PDL "
-                       "chained, attention / lm_head left out), distinct weights per launch (810 MB per replay > L2)",
-                "step_level": {"bitlinear_GBs_over_whole_step": bb["per_step"] / (ms / K * 1e-3) / 1e9,
-                               "frac": bb["per_step"] / (ms / K * 1e-3) / 1e9 / peak}}
     cpu = cpu_decode_baseline(cfg, B, tokens=3) if world == 1 else None
-    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
-            "data": "synthetic",
-            "config": {"workload": f"{name} greedy decode, batch {B} per GPU, {prompt_len}-token prompt then {K} "
+    line = {"metric": metric, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8" if B <= 4 else "f16", "data": "synthetic",
+            "config": {"workload": f"{name} greedy decode, batch {B} per GPU, {main_res['prompt_len']}-token prompt then {K} "
                                    f"generated tokens, static KV cache, one CUDA-graph replay per step",
                        "replicas": world, "l2": "per-step weight stream 1.07 GB > 126 MB L2 (no flush needed)",
-                       "activation_dtype": "fp32 residual / fp16 KV cache / 23-bit integer BitLinear inputs"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8 * B,
-                    "ms_per_step": ms_e2e / K},
-            "gpu_launches": dec.launches_per_step() * K, "launches_per_step": dec.launches_per_step(),
-            "roofline": roofline, "clocks": clocks}
+                       "activation_dtype": ("fp32 residual / fp16 KV cache / 23-bit integer BitLinear inputs" if B <= 4 else
+                                            "fp32 residual / fp16 KV cache / fp16 BitLinear inputs (tcgen05 kind::f16, fp32 accumulate)")},
+            "e2e": main_res["e2e"],
+            "gpu_launches": main_res["launches_per_step"] * K, "launches_per_step": main_res["launches_per_step"],
+            "roofline": main_res["roofline"], "clocks": clocks}
+    line.update(extra)
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

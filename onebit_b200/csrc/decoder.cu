@@ -804,11 +804,12 @@ int tc5_ksplit(int row_tiles, int K, int ksplit_max) {
 // grid.z), the glue kernels hand it fp16 activations, a reduce pass sums the K splits and emits the LayerNorm statistics.
 // Per layer: glue | q,k,v (one launch) | reduce | attention | glue | o | reduce | glue | gate,up (one launch) | reduce |
 // glue | down | reduce = 13 launches.
-int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int* cur_io) {
+int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int* cur_io, bool only_proj = false) {
     const onebit_decoder_config& C = D->cfg;
     const int H = C.hidden_size, I = C.intermediate_size, pd = C.param_dtype, B = C.max_batch;
     int cur = *cur_io, rc;
     auto reduce = [&](float* t0, float* t1, float* t2, int n, int nprob, int S, float* stats) -> int {
+        if (only_proj) return ONEBIT_OK;
         ReduceArgs r = {};
         r.t[0] = t0; r.t[1] = t1; r.t[2] = t2; r.N[0] = r.N[1] = r.N[2] = n; r.stats = stats; r.M = M; r.S = S;
         ++*launches;
@@ -824,7 +825,7 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         g.t_a = D->t_d; g.stats_a = D->red_d; g.ncta_a = kReduceSlices;
         g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1];
         g.embed = D->embed; g.ids = D->ids; g.ln_w = P.input_layernorm; g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
-        rc = glue_launch(D, g, s); if (rc) return rc; ++*launches;
+        if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
         cur ^= 1;
         // ---- q, k, v
         Tc5Launch t = {};
@@ -850,12 +851,14 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
         // many (sequence, head) CTAs: stream the cached rows from L2 instead of staging them (several CTAs per SM)
         at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = 0;
-        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), (size_t)std::max(C.max_seq_len, 4 * kHeadDim) * sizeof(float), s, at);
-        if (rc) return rc; ++*launches;
+        if (!only_proj) {
+            rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), (size_t)std::max(C.max_seq_len, 4 * kHeadDim) * sizeof(float), s, at);
+            if (rc) return rc; ++*launches;
+        }
         // ---- glue 2: attention output -> fp16
         g = {};
         g.mode = GLUE_PLAIN; g.M = M; g.K = H; g.nprob = 1; g.x_plain = D->attn_out; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
-        rc = glue_launch(D, g, s); if (rc) return rc; ++*launches;
+        if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
         // ---- o_proj
         t = {};
         t.x16 = D->x_f16; t.M = M; t.K = H; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, H, D->ksplit_max);
@@ -868,7 +871,7 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         g.t_a = D->t_o; g.stats_a = D->red_o; g.ncta_a = kReduceSlices;
         g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = P.post_attention_layernorm;
         g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
-        rc = glue_launch(D, g, s); if (rc) return rc; ++*launches;
+        if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
         cur ^= 1;
         // ---- gate, up
         t = {};
@@ -889,7 +892,7 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         g.t_a = tg[0]; g.stats_a = D->red_gu; g.ncta_a = kReduceSlices;
         g.t_b = tg[1]; g.stats_b = D->red_gu + (size_t)kReduceSlices * M * 2; g.ncta_b = kReduceSlices;
         g.ln_eps = C.ln_eps;
-        rc = glue_launch(D, g, s); if (rc) return rc; ++*launches;
+        if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
         // ---- down_proj
         t = {};
         t.x16 = D->xI_f16; t.M = M; t.K = I; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, I, D->ksplit_max);
@@ -1235,6 +1238,10 @@ int onebit_decoder_gemv_only(onebit_decoder* D, int batch, void* stream) {
     const int uH = H / imma::kUnitCols, uI = I / imma::kUnitCols;
     const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
     const size_t dgH = (size_t)C.max_batch * uH * imma::kUnitBytes;
+    if (D->ksplit_max > 1 && M > 4) {  // batched decode: the projection launches of the tcgen05 path alone
+        int launches = 0, cur = 0;
+        return run_tc5_layers(D, M, s, &launches, &cur, /*only_proj=*/true);
+    }
     {
         int launches = 0, cur = 0, nc_d = cH;
         bool used = false;

@@ -208,3 +208,31 @@ def test_persistent_single_kernel_step_matches_the_reference_fixture():
         assert out[f"persistent_{nm}"] and out[f"status_{nm}"] == 0, out
         assert out[f"logits_rel_l2_{nm}"] < 2e-3 and out[f"greedy_agree_{nm}"] == 1.0 and out[f"batch_invariant_{nm}"], out
         assert abs(out[f"ppl_{nm}"] - out["ppl_ref"]) / out["ppl_ref"] < 1e-4, out
+
+
+# ---- batched decode (5..64 sequences per replica): tcgen05 path inside the decoder ----
+@pytest.mark.parametrize("model,layers,batch", [("7b", 2, 32), ("13b", 1, 64), ("7b", 1, 8)])
+def test_batched_decode_on_the_tcgen05_path_matches_the_reference_port(model, layers, batch):
+    """Decode batches the bit-plane GEMV cannot hold run every BitLinear on the tcgen05 decode tile (fp16 activations,
+    fp32 accumulation): logits of a teacher-forced 3-token pass vs oracle/ref_port.py at real LLaMA widths."""
+    out = _wide(model, layers, 3, batch, "f16")
+    assert out["status"] == 0 and not out["persistent"]
+    assert out["launches"] == layers * 13 + 4, out  # 13 launches per layer + final glue, lm_head, argmax, forced-id copy
+    assert out["rel_l2"] < 2e-3, out
+    assert out["argmax_agree"] > 0.97, out  # fp16 activations: a near-tie among 32000 random logits may flip
+
+
+def test_batched_decode_tiny_model_against_the_reference_fixture(tiny):
+    """8 sequences (the fixture's two, four times over) through the batched path vs the reference's own logits."""
+    config, sd, z = tiny
+    ids = torch.from_numpy(z["input_ids"])[:, :24]
+    ids8 = torch.cat([ids, ids.flip(0), ids, ids.flip(0)], dim=0)
+    want = torch.from_numpy(z["logits"])[:, :24]
+    want8 = torch.cat([want, want.flip(0), want, want.flip(0)], dim=0).numpy()
+    dec = BitLlamaDecoderB200(config, sd, max_seq_len=64, max_batch=8, param_dtype=torch.float16)
+    got = dec.forward_tokens(ids8).cpu().numpy()
+    assert dec.launches_per_step() == 2 * 13 + 4
+    dec.close()
+    assert oracle.rel_l2(got, want8) < 3e-3
+    for b in range(8):
+        assert oracle.rel_l2(got[b], want8[b]) < 5e-3
