@@ -100,6 +100,14 @@ __device__ __forceinline__ uint2 ldg_nc_u2(const uint8_t* p) {
     return r;
 }
 
+#ifdef ONEBIT_TC5_TRACE
+__device__ unsigned long long g_tc5_trace[512];
+__device__ __forceinline__ unsigned long long tc5_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TC5_STAMP(cond, slot) do { if ((cond) && (slot) < 512) g_tc5_trace[(slot)] = tc5_now(); } while (0)
+#else
+#define TC5_STAMP(cond, slot) do { } while (0)
+#endif
+
 struct Tc5Problem {
     const uint8_t* w;   // [N][K/8] packed signs (unused by the DENSE variant)
     const __half* h;    // [K] fp16 input_factor
@@ -127,6 +135,8 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     __shared__ uint4 h_stage[TL::kHStage];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool tr0 = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    TC5_STAMP(tr0 && threadIdx.x == 0, 0);
     int pi = 0;
 #pragma unroll
     for (int i = 1; i < kMaxProblems; ++i)
@@ -158,6 +168,7 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    TC5_STAMP(tr0 && threadIdx.x == 0, 1);
 
     if (warp == 0) {
         // ===== TMA producer: x tile [256 tokens][64 k] per stage =====
@@ -181,6 +192,7 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                 const int s = c % kStages, ph = (c / kStages) & 1;
                 mbar_wait(&full_a[s], ph);
                 mbar_wait(&full_b[s], ph);
+                TC5_STAMP(tr0 && c < 40, 18 + 4 * c);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(sA + s * kABytes), b_addr = smem_u32(sB + s * kBBytes);
 #pragma unroll
@@ -193,6 +205,7 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                     }
                 }
                 umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+                TC5_STAMP(tr0 && c < 40, 19 + 4 * c);
             }
             umma_commit(&tmem_full);
         }
@@ -236,6 +249,7 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             // 8 x 16 B of input_factor, the same for every row: from the staged slice (decode) or through L1 (prefill)
             const uint4* hp = h_staged ? h_stage + c * 8 : reinterpret_cast<const uint4*>(P.h + (size_t)(c_begin + c) * kChunkK);
             if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+            TC5_STAMP(tr0 && e == 0 && c < 40, 16 + 4 * c);
             unsigned char* base = sA + s * kABytes;
 #pragma unroll
             for (int half = 0; half < HALVES; ++half) {
@@ -258,10 +272,12 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
             mbar_arrive(&full_a[s]);
+            TC5_STAMP(tr0 && e == 0 && c < 40, 17 + 4 * c);
           }
         }
         // ===== epilogue: TMEM -> registers -> * g -> t[m][n] (lanes = consecutive n: coalesced) =====
         mbar_wait(&tmem_full, 0);
+        TC5_STAMP(tr0 && threadIdx.x == 64, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
 #pragma unroll 1
@@ -292,8 +308,10 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             }
         }
     }
+    TC5_STAMP(tr0 && threadIdx.x == 64, 3);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    TC5_STAMP(tr0 && threadIdx.x == 0, 4);
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TL::kTmemCols) : "memory");
 }
 
@@ -439,3 +457,15 @@ int launch_dense_tc5(const __half* x16, const __half* w16, float* out, int64_t m
 }
 
 }  // namespace onebit
+
+// Debug only (side builds with -DONEBIT_TC5_TRACE): %globaltimer stamps of CTA (0,0,0) of the LAST tcgen05 launch:
+// [0] kernel start, [1] setup done, [2] accumulators complete, [3] epilogue done, [4] CTA end; per K chunk c < 40 at
+// 16 + 4c: expander stage free / expander done / MMA inputs ready / MMA issued.
+extern "C" __attribute__((visibility("default"))) int onebit_debug_tc5_trace(unsigned long long* out512) {
+#ifdef ONEBIT_TC5_TRACE
+    return cudaMemcpyFromSymbol(out512, onebit::g_tc5_trace, sizeof(unsigned long long) * 512) == cudaSuccess ? 0 : -2;
+#else
+    (void)out512;
+    return -1;
+#endif
+}
