@@ -30,7 +30,8 @@ namespace {
 //             5..64 sequences: many small CTAs (4 per SM, 53 KB each) so that all 148 SMs stream and expand weights.
 // DENSE = true replaces the sign expanders by a second TMA stream of a dense fp16 matrix (lm_head for those batches).
 constexpr int kChunkK = 64;     // K columns per pipeline stage (= one 128-byte swizzle row of fp16)
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;    // warp 0 TMA, warp 1 MMA, warps 2-9 sign expanders (warps 2-5 also run the epilogue)
+constexpr int kExpanders = 256;
 constexpr int kMaxProblems = 3; // projections that share the activation tile in one launch (q/k/v, gate/up)
 template <int HALVES, int TM>
 struct Tile {
@@ -39,7 +40,9 @@ struct Tile {
     static constexpr int kHStage = HALVES == 2 ? 1 : 256;  // uint4 slots of shared memory for the CTA's slice of input_factor (decode)
     static constexpr int kABytes = kTileN * kChunkK * 2;
     static constexpr int kBBytes = TM * kChunkK * 2;
-    static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024;  // + alignment slack
+    static constexpr int kSlabChunks = 8;                                  // K chunks per weight slab
+    static constexpr int kSlabBytes = kTileN * kSlabChunks * 8;            // [rows][64 B of packed signs]
+    static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 2 * kSlabBytes + 1024;  // + alignment slack
     static constexpr int kTmemCols = HALVES * TM < 32 ? 32 : HALVES * TM;       // power of two for these configurations
 };
 
@@ -118,11 +121,13 @@ struct Tc5Problem {
 struct PrefillArgs {
     Tc5Problem p[kMaxProblems];
     int nprob, M, K, ksplit;
+    int wtma;  // packed signs arrive through TMA slabs (K % 128 == 0); else the expanders load them themselves
 };
 
 template <typename TP, int HALVES, int TM, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap amap,
+                   const __grid_constant__ CUtensorMap wmap1, const __grid_constant__ CUtensorMap wmap2,
                    const __grid_constant__ PrefillArgs A) {
     using TL = Tile<HALVES, TM>;
     constexpr int kTileN = TL::kTileN, kTileM = TM, kStages = TL::kStages, kABytes = TL::kABytes, kBBytes = TL::kBBytes;
@@ -130,7 +135,8 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sA = smem;                          // [stage][HALVES * 128 rows][128 B] swizzled
     unsigned char* sB = smem + kStages * kABytes;      // [stage][TM rows][128 B] swizzled (TMA)
-    __shared__ __align__(8) uint64_t full_a[kStages], full_b[kStages], empty[kStages], tmem_full;
+    unsigned char* sW = sB + kStages * kBBytes;        // [2][HALVES * 128 rows][64 B] packed-sign slabs of 8 chunks (TMA)
+    __shared__ __align__(8) uint64_t full_a[kStages], full_b[kStages], empty[kStages], tmem_full, wfull[2], wempty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint4 h_stage[TL::kHStage];
 
@@ -144,19 +150,26 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     const Tc5Problem& P = A.p[pi];
     const int n0 = ((int)blockIdx.x - P.tile_begin) * kTileN, m0 = blockIdx.y * kTileM;
     const int nchunks_all = A.K / kChunkK;
-    const int c_begin = (int)(((long long)nchunks_all * blockIdx.z) / A.ksplit);
-    const int nchunks = (int)(((long long)nchunks_all * (blockIdx.z + 1)) / A.ksplit) - c_begin;  // this CTA's K slice
+    // this CTA's K slice; slices start on even chunks (16-byte aligned packed-sign columns for the TMA slabs)
+    const int half_all = nchunks_all >> 1;
+    const int c_begin = 2 * (int)(((long long)half_all * blockIdx.z) / A.ksplit);
+    const int c_end = (int)blockIdx.z + 1 == A.ksplit ? nchunks_all : 2 * (int)(((long long)half_all * (blockIdx.z + 1)) / A.ksplit);
+    const int nchunks = c_end - c_begin;
     float* tout = P.t + (size_t)blockIdx.z * A.M * P.N;
     const int m_valid = min(kTileM, A.M - m0);
     const int umma_n = max(16, (m_valid + 15) & ~15);  // tokens covered by the MMA (multiple of 16)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_a[s], DENSE ? 1 : 128);
+            mbar_init(&full_a[s], DENSE ? 1 : kExpanders);
             mbar_init(&full_b[s], 1);
             mbar_init(&empty[s], 1);
         }
         mbar_init(&tmem_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&wfull[s], 1);
+            mbar_init(&wempty[s], kExpanders);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
     }
@@ -173,8 +186,23 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer: x tile [256 tokens][64 k] per stage =====
         if (lane == 0) {
+            // packed signs: 64-byte-wide slabs (8 chunks) of the CTA's rows, two slabs ahead of the expanders. They come
+            // through TMA because a global load in flight in an expander thread would be waited for by the MEMBAR that
+            // fence.proxy.async implies: one HBM round trip per chunk (measured 0.75 us per chunk, tools/trace_tc5.py).
+            const CUtensorMap* wm = pi == 0 ? &amap : (pi == 1 ? &wmap1 : &wmap2);
+            const int nslabs = (nchunks + TL::kSlabChunks - 1) / TL::kSlabChunks;
+            auto issue_slab = [&](int j) {
+                if (DENSE || !A.wtma || j >= nslabs) return;
+                const int b = j & 1;
+                if (j >= 2) mbar_wait(&wempty[b], ((j >> 1) - 1) & 1);
+                mbar_expect_tx(&wfull[b], TL::kSlabBytes);
+                tma_load_2d(sW + b * TL::kSlabBytes, wm, (c_begin + j * TL::kSlabChunks) * 8, n0, &wfull[b]);
+            };
+            issue_slab(0);
+            issue_slab(1);
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % kStages, it = c / kStages;
+                if (c > 0 && (c % TL::kSlabChunks) == 0) issue_slab(c / TL::kSlabChunks + 1);
                 if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
                 mbar_expect_tx(&full_b[s], kBBytes);
                 tma_load_2d(sB + s * kBBytes, &xmap, (c_begin + c) * kChunkK, m0, &full_b[s]);
@@ -210,58 +238,63 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             umma_commit(&tmem_full);
         }
     } else {
-        // ===== sign expanders: thread e (0..127) owns rows e and e + 128 of the CTA's weight tile =====
-        const int e = threadIdx.x - 64;
+        // ===== sign expanders: 256 threads. Prefill tile (256 rows): thread e2 owns row e2, all 64 columns of a chunk.
+        // Decode tile (128 rows): threads e2 and e2 + 128 share row e2 & 127, 32 columns each (a lone warp per scheduler
+        // runs the ~100 dependent instructions of a row-chunk at ~6 cycles each: more threads, shorter chains) =====
+        const int e2 = threadIdx.x - 64;
+        const int e = HALVES == 2 ? e2 : (e2 & 127);           // row of the CTA tile
+        const int q_lo = HALVES == 2 ? 0 : 4 * (e2 >> 7);      // first 16-byte group (8 columns each) of the chunk
+        constexpr int kQ = HALVES == 2 ? 8 : 4;                // groups per thread and chunk
         const int Kb = A.K >> 3;
         const uint8_t* wrow0 = P.w + (size_t)min(n0 + e, P.N - 1) * Kb + (size_t)c_begin * 8;
-        const uint8_t* wrow1 = P.w + (size_t)min(n0 + e + 128, P.N - 1) * Kb + (size_t)c_begin * 8;
         const bool h_staged = !DENSE && TL::kHStage > 1 && nchunks * 8 <= TL::kHStage;
         if (h_staged) {  // the CTA's K slice of input_factor: one cooperative copy instead of 8 L1/L2 round trips per chunk
             const uint4* hsrc = reinterpret_cast<const uint4*>(P.h + (size_t)c_begin * kChunkK);
-            for (int i = e; i < nchunks * 8; i += 128) h_stage[i] = __ldg(hsrc + i);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = e2; i < nchunks * 8; i += kExpanders) h_stage[i] = __ldg(hsrc + i);
+            asm volatile("bar.sync 1, %0;" ::"n"(kExpanders) : "memory");
         }
-        // The 8 weight bytes of a row and chunk come straight from HBM: keep kPF chunks of them in flight in registers, so
-        // that an iteration never waits a full memory round trip (the decode configuration has no long MMA to hide it)
-        constexpr int kPF = 8;
-        uint2 q0[kPF], q1[kPF];
+        constexpr int kPF = 8;  // = TL::kSlabChunks: chunks per slab / per register refill
+        uint2 q0[kPF];
 #pragma unroll
         for (int i = 0; i < kPF; ++i) {
             q0[i] = make_uint2(0u, 0u);
-            q1[i] = make_uint2(0u, 0u);
-            if (!DENSE && i < nchunks) {
-                q0[i] = ldg_nc_u2(wrow0 + i * 8);
-                if (HALVES == 2) q1[i] = ldg_nc_u2(wrow1 + i * 8);
-            }
+            if (!DENSE && !A.wtma && i < nchunks) q0[i] = ldg_nc_u2(wrow0 + i * 8);  // legacy path (K % 128 != 0): own loads
         }
         for (int cb = 0; !DENSE && cb < nchunks; cb += kPF) {
+          if (A.wtma) {  // this thread's 64 bytes (8 chunks) of rows e / e + 128 from the slab, then the slab is free again
+            const int j = cb / kPF, b = j & 1;
+            mbar_wait(&wfull[b], (j >> 1) & 1);
+            const uint4* rp = reinterpret_cast<const uint4*>(sW + b * TL::kSlabBytes + e * 64);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 v = rp[i];
+                q0[2 * i] = make_uint2(v.x, v.y);
+                q0[2 * i + 1] = make_uint2(v.z, v.w);
+            }
+            mbar_arrive(&wempty[b]);
+          }
 #pragma unroll
           for (int ci = 0; ci < kPF; ++ci) {
             const int c = cb + ci;
             if (c >= nchunks) break;
             const int s = c % kStages, it = c / kStages;
-            const uint2 w0 = q0[ci];
-            const uint2 w1 = q1[ci];
-            if (c + kPF < nchunks) {  // refill the slot with the chunk kPF ahead
-                q0[ci] = ldg_nc_u2(wrow0 + (c + kPF) * 8);
-                if (HALVES == 2) q1[ci] = ldg_nc_u2(wrow1 + (c + kPF) * 8);
-            }
+            const uint2 w = q0[ci];
+            if (!A.wtma && c + kPF < nchunks) q0[ci] = ldg_nc_u2(wrow0 + (c + kPF) * 8);  // refill with the chunk kPF ahead
             // 8 x 16 B of input_factor, the same for every row: from the staged slice (decode) or through L1 (prefill)
             const uint4* hp = h_staged ? h_stage + c * 8 : reinterpret_cast<const uint4*>(P.h + (size_t)(c_begin + c) * kChunkK);
             if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
-            TC5_STAMP(tr0 && e == 0 && c < 40, 16 + 4 * c);
+            TC5_STAMP(tr0 && e2 == 0 && c < 40, 16 + 4 * c);
             unsigned char* base = sA + s * kABytes;
-#pragma unroll
-            for (int half = 0; half < HALVES; ++half) {
-                const uint2 w = half ? w1 : w0;
-                const int r = e + half * 128;
+            {
+                const int r = e;
                 unsigned char* rowp = base + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {  // 16-byte chunk q = columns 8q .. 8q+7 = byte q of the 64-bit word
+                for (int qi = 0; qi < kQ; ++qi) {  // 16-byte group q = columns 8q .. 8q+7 = byte q of the 64-bit word
+                    const int q = q_lo + qi;
                     const uint4 hv = h_staged ? hp[q] : __ldg(hp + q);
                     // byte q of the row chunk: bit i = column 8q + i. An 8-bit value times (0x40008000 >> 2i) is two
                     // disjoint shifted copies (no carries): bit 2i lands on bit 15, bit 2i+1 on bit 31.
-                    const uint32_t b8 = __byte_perm(q < 4 ? w.x : w.y, 0u, 0x4440u | (uint32_t)(q & 3));
+                    const uint32_t b8 = (((q < 4 ? w.x : w.y) >> (8 * (q & 3))) & 0xFFu);
                     uint4 o;
                     o.x = ((b8 * 0x40008000u) & 0x80008000u) ^ hv.x;
                     o.y = ((b8 * 0x10002000u) & 0x80008000u) ^ hv.y;
@@ -270,9 +303,11 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                     *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) << 4)) = o;  // SWIZZLE_128B: chunk ^= row % 8
                 }
             }
+            TC5_STAMP(tr0 && e2 == 0 && c < 40, 256 + 2 * c);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+            TC5_STAMP(tr0 && e2 == 0 && c < 40, 257 + 2 * c);
             mbar_arrive(&full_a[s]);
-            TC5_STAMP(tr0 && e == 0 && c < 40, 17 + 4 * c);
+            TC5_STAMP(tr0 && e2 == 0 && c < 40, 17 + 4 * c);
           }
         }
         // ===== epilogue: TMEM -> registers -> * g -> t[m][n] (lanes = consecutive n: coalesced) =====
@@ -280,12 +315,13 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         TC5_STAMP(tr0 && threadIdx.x == 64, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int grp = (warp - 2) >> 2;  // two warps per quarter: they split the halves (prefill) or the token columns (decode)
 #pragma unroll 1
-        for (int half = 0; half < HALVES; ++half) {
+        for (int half = (HALVES == 2 ? grp : 0); half < (HALVES == 2 ? grp + 1 : 1); ++half) {
             const int n = n0 + half * 128 + quarter * 32 + lane;
             const float gs = (P.g != nullptr && n < P.N) ? to_f32(static_cast<const TP*>(P.g)[n]) : 1.f;
 #pragma unroll 1
-            for (int cb = 0; cb < umma_n; cb += 32) {
+            for (int cb = (HALVES == 2 ? 0 : 32 * grp); cb < umma_n; cb += (HALVES == 2 ? 32 : 64)) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * TM + cb);
                 asm volatile(
@@ -352,8 +388,23 @@ int encode_2d(CUtensorMap* map, const __half* base, int64_t rows, int64_t k, int
     return ONEBIT_OK;
 }
 
+// packed signs [N][K/8] as a 2-D byte tensor: boxes of 64 bytes (8 K chunks) x box_rows rows, no swizzle
+int encode_w(CUtensorMap* map, const uint8_t* base, int64_t rows, int64_t kb, int box_rows) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return fail(ONEBIT_ERR_CUDA, "tcgen05 path: cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[2] = {(cuuint64_t)kb, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kb};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(ONEBIT_ERR_CUDA, "tcgen05 path: cuTensorMapEncodeTiled (weights) failed, code " + std::to_string((int)cr));
+    return ONEBIT_OK;
+}
+
 template <typename TP, int HALVES, int TM, bool DENSE>
-int launch_inst(const CUtensorMap& xmap, const CUtensorMap& amap, const PrefillArgs& a, dim3 grid, cudaStream_t s) {
+int launch_inst(const CUtensorMap& xmap, const CUtensorMap* wm, const PrefillArgs& a, dim3 grid, cudaStream_t s) {
     auto kern = prefill_tc5_kernel<TP, HALVES, TM, DENSE>;
     static bool configured[64] = {false};
     int dev = 0;
@@ -362,7 +413,7 @@ int launch_inst(const CUtensorMap& xmap, const CUtensorMap& amap, const PrefillA
         ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<HALVES, TM>::kSmemBytes));
         configured[dev] = true;
     }
-    kern<<<grid, kThreads, Tile<HALVES, TM>::kSmemBytes, s>>>(xmap, amap, a);
+    kern<<<grid, kThreads, Tile<HALVES, TM>::kSmemBytes, s>>>(xmap, wm[0], wm[1], wm[2], a);
     ONEBIT_CUDA_TRY(cudaGetLastError());
     return ONEBIT_OK;
 }
@@ -427,17 +478,29 @@ int launch_tc5(const Tc5Launch& L, cudaStream_t s) {
     if (rc) return rc;
     PrefillArgs a = {};
     a.nprob = L.nprob; a.M = L.M; a.K = L.K; a.ksplit = L.ksplit;
+    a.wtma = (L.K % 128 == 0) ? 1 : 0;
+    ONEBIT_REQUIRE(L.ksplit == 1 || L.K / kChunkK / 2 >= L.ksplit, "launch_tc5: K too small for this split");
+    CUtensorMap wm[3];
     int tiles = 0;
     for (int i = 0; i < L.nprob; ++i) {
         a.p[i].w = reinterpret_cast<const uint8_t*>(L.p[i].w); a.p[i].h = L.p[i].h16; a.p[i].g = L.p[i].g; a.p[i].t = L.p[i].t;
         a.p[i].N = L.p[i].N; a.p[i].tile_begin = tiles;
         tiles += (L.p[i].N + tile_n - 1) / tile_n;
+        if (!aligned16(L.p[i].w)) a.wtma = 0;
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (a.wtma && i < L.nprob) {
+            rc = encode_w(&wm[i], a.p[i].w, a.p[i].N, L.K / 8, tile_n);
+            if (rc) return rc;
+        } else {
+            wm[i] = xmap;  // unused slot
+        }
     }
     dim3 grid((unsigned)tiles, (unsigned)((L.M + tile_m - 1) / tile_m), (unsigned)L.ksplit);
     ONEBIT_REQUIRE(grid.y <= 65535, "prefill_tc5: M too large (max 16.7M tokens)");
     return dispatch_dtype(L.param_dtype, [&](auto pt) {
         using TP = decltype(pt);
-        return small ? launch_inst<TP, 1, 64, false>(xmap, xmap, a, grid, s) : launch_inst<TP, 2, 256, false>(xmap, xmap, a, grid, s);
+        return small ? launch_inst<TP, 1, 64, false>(xmap, wm, a, grid, s) : launch_inst<TP, 2, 256, false>(xmap, wm, a, grid, s);
     });
 }
 
@@ -453,7 +516,8 @@ int launch_dense_tc5(const __half* x16, const __half* w16, float* out, int64_t m
     a.nprob = 1; a.M = (int)m; a.K = (int)k; a.ksplit = 1;
     a.p[0].t = out; a.p[0].N = (int)n; a.p[0].tile_begin = 0;
     dim3 grid((unsigned)((n + 127) / 128), 1, 1);
-    return launch_inst<__half, 1, 64, true>(xmap, amap, a, grid, s);
+    const CUtensorMap wm[3] = {amap, xmap, xmap};
+    return launch_inst<__half, 1, 64, true>(xmap, wm, a, grid, s);
 }
 
 }  // namespace onebit

@@ -27,6 +27,8 @@ t = buf.astype(np.int64)
 t0 = t[0]
 print(f"M={M} K={K} N={N}: setup {t[1]-t0} ns, accumulators done {t[2]-t0}, epilogue done {t[3]-t0}, CTA end {t[4]-t0}")
 n = K // 64
-for c in range(min(n, 40)):
+for c in range(min(n, 12)):
     a = t[16 + 4 * c: 20 + 4 * c] - t0
-    print(f"  chunk {c:2d}: stage free {a[0]:6d}  expanded {a[1]:6d} (+{a[1]-a[0]:5d})  mma inputs ready {a[2]:6d}  mma issued {a[3]:6d}")
+    f0, f1 = t[256 + 2 * c] - t0, t[257 + 2 * c] - t0
+    print(f"  chunk {c:2d}: stage free {a[0]:6d}  stores issued {f0:6d} (+{f0-a[0]:4d})  fence done {f1:6d} (+{f1-f0:4d})  arrived {a[1]:6d}  "
+          f"mma inputs ready {a[2]:6d}  mma issued {a[3]:6d}")
