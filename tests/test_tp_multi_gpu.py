@@ -1,9 +1,9 @@
 """Tensor-parallel decode on real GPUs (needs >= 2 devices; skipped otherwise — the single-GPU round-end run skips it).
 Launches tools/tp_check.py under torchrun with a hard timeout so that a communication problem cannot hang the suite.
 
-Status (round 1): the host-side sharding and the collective plumbing are verified on CPU (tests/test_tp_gloo_cpu.py);
-two 2-GPU attempts of this check did not finish inside their time limits and the round's GPU budget ended before the
-cause could be isolated, so the tensor-parallel decode path is NOT yet verified on hardware."""
+Status (round 2): verified on 2 x B200 — tiny-model logits rel-L2 4.4e-4 vs the reference fixture, eager and CUDA-graphed.
+The round-1 "hang" was torch's destroy_process_group() blocking at exit while graphs with captured NCCL kernels existed;
+tools/tp_check.py now leaves through os._exit after a barrier."""
 import subprocess
 import sys
 from pathlib import Path
@@ -18,8 +18,6 @@ ROOT = Path(__file__).resolve().parent.parent
 import os
 
 
-@pytest.mark.skipif(os.environ.get("ONEBIT_RUN_TP_TEST", "0") != "1",
-                    reason="tensor-parallel decode is not yet verified on hardware: opt in with ONEBIT_RUN_TP_TEST=1")
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_tp2_tiny_model_matches_reference_logits():
     cmd = ["timeout", "240", sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",

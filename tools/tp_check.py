@@ -2,7 +2,8 @@
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/tp_check.py
 1) tiny model vs the reference golden logits with tp = world size (eager and CUDA-graphed);
 2) LLaMA-7B-shaped timing of the TP decode step (random weights)."""
-import json, os, sys, time
+import faulthandler, json, os, sys, time
+faulthandler.dump_traceback_later(int(os.environ.get('ONEBIT_TP_WATCHDOG_S', '90')), exit=True)  # a hang prints every thread's Python stack and exits
 from pathlib import Path
 import numpy as np
 import torch
@@ -27,17 +28,33 @@ for graph in (False, True):
         print(f"tp_check: tiny model, graph={graph}", flush=True)
     dec = BitLlamaDecoderB200(config, sd, device=dev, max_seq_len=64, max_batch=2, param_dtype=torch.float32,
                               use_graph=graph, tp_group=dist.group.WORLD)
+    print(f"tp_check[{rank}]: decoder created (launch path: fused stages, tp={world})", flush=True)
+    dec.reset(ids[:, 0])
+    torch.cuda.synchronize()
+    print(f"tp_check[{rank}]: warm-up steps done", flush=True)
     logits = dec.forward_tokens(ids).cpu().numpy()
+    print(f"tp_check[{rank}]: forward_tokens done", flush=True)
     res["graph" if graph else "eager"] = oracle.rel_l2(logits, z["logits"][:, :24])
     dec.close()
+    dec._graphs.clear()  # captured NCCL kernels must be gone before the process group is torn down
+    del dec
 ok = all(v < 2e-3 for v in res.values())
 if rank == 0:
     print(json.dumps({"tp": world, "tiny_model_logits_rel_l2": res, "parity_ok": ok}), flush=True)
+def finish(code):
+    # destroy_process_group() blocks forever when CUDA graphs that captured NCCL kernels are (or were) alive in the process
+    # (measured: both ranks parked in destroy_process_group, round-2 gpurun call 28): synchronise, then leave without it
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(code)
+
+
 if os.environ.get("ONEBIT_TP_TIMING", "0") != "1":
-    dist.barrier(); dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
-# timing at LLaMA-7B widths (ONEBIT_TP_TIMING=1)
-cfg7 = dict(LLAMA_7B)
+    finish(0 if ok else 1)
+# timing at LLaMA-7B / LLaMA2-13B widths (ONEBIT_TP_TIMING=1, ONEBIT_TP_MODEL=7b|13b)
+from onebit_b200 import LLAMA2_13B
+cfg7 = dict(LLAMA2_13B if os.environ.get("ONEBIT_TP_MODEL", "7b") == "13b" else LLAMA_7B)
 dec = BitLlamaDecoderB200(cfg7, synthetic_state_dict(cfg7, seed=0), device=dev, max_seq_len=256, max_batch=1,
                           tp_group=dist.group.WORLD)
 dec.reset(torch.tensor([5]))
@@ -51,7 +68,6 @@ for _ in range(64):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 64
 if rank == 0:
-    print(json.dumps({"tp": world, "tiny_model_logits_rel_l2": res, "parity_ok": ok, "llama7b_tp_ms_per_step": ms,
-                      "llama7b_tp_tok_s": 1e3 / ms, "launches_per_step": dec.launches_per_step()}), flush=True)
-dist.barrier(); dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+    print(json.dumps({"tp": world, "model": os.environ.get("ONEBIT_TP_MODEL", "7b"), "tiny_model_logits_rel_l2": res, "parity_ok": ok,
+                      "tp_ms_per_step": ms, "tp_tok_s": 1e3 / ms, "launches_per_step": dec.launches_per_step()}), flush=True)
+finish(0 if ok else 1)
