@@ -181,8 +181,16 @@ ONEBIT_API int onebit_decoder_kernel_launches_per_step(onebit_decoder* dec);
 /* Persistent single-kernel step (experimental, opt-in with ONEBIT_PERSIST=1; batch <= 2, tp_size == 1): 1 if this
  * decoder uses it. */
 ONEBIT_API int onebit_decoder_is_persistent(onebit_decoder* dec);
+/* Tensor parallelism without a library collective: switch the decoder's all-reduces (partial sums of o_proj / down_proj,
+ * LayerNorm statistics of q/k/v and gate/up — SURVEY.md 8e; the reference has no tensor parallelism for BitLinearInf) from the
+ * callback to a one-shot Lamport all-reduce over NVLink peer memory. peer_buffers[r] = rank r's symmetric buffer of
+ * buffer_bytes bytes, addressable from this device (e.g. torch.distributed._symmetric_memory buffer_ptrs), filled with
+ * -0.0f on every rank BEFORE any rank steps; buffer_bytes >= 3 * nranks * max_batch * hidden_size * 4. */
+ONEBIT_API int onebit_decoder_enable_p2p_allreduce(onebit_decoder* dec, int rank, int nranks, void* const* peer_buffers,
+                                                   size_t buffer_bytes);
 /* Health of the persistent step (synchronous device read): 0 = fine, 1 = an in-kernel exchange timed out,
- * 2 = a step was asked to decode past max_seq_len (it wrote nothing outside the cache). */
+ * 2 = a step was asked to decode past max_seq_len (it wrote nothing outside the cache), 3 = a peer's data did not
+ * arrive in the one-shot tensor-parallel all-reduce. */
 ONEBIT_API int onebit_decoder_status(onebit_decoder* dec, int* code);
 /* Device time stamps (ns, %globaltimer) recorded by two CTAs of the persistent step (the first and the last) during
  * the LAST step: layout [2 tracers][L + 2 rows][160 slots]. Row 0: [0] kernel start. Row 1 + l (layer l): [0] layer start,

@@ -12,6 +12,7 @@ There is no PyTorch fallback: every arithmetic step runs in hand-written sm_100a
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -119,6 +120,9 @@ class BitLlamaDecoderB200:
                                                 final_norm.data_ptr(), lm_head.data_ptr(), cos.data_ptr(), sin.data_ptr(),
                                                 self._ar_cb if self._ar_cb is not None else _lib.ALLREDUCE_FN(0), None)
         _lib.check(rc, "onebit_decoder_create")
+        self.tp_allreduce = "none" if self.tp_size == 1 else "nccl"
+        if self.tp_size > 1 and os.environ.get("ONEBIT_TP_ALLREDUCE", "p2p") != "nccl":
+            self._enable_p2p_allreduce(tp_group)
         self.logits = torch.zeros((self.max_batch, self.V), dtype=torch.float32, device=dev)
         self.forced = torch.zeros((self.max_batch,), dtype=torch.int64, device=dev)
         self._graphs = {}
@@ -126,6 +130,27 @@ class BitLlamaDecoderB200:
         self.batch = 0
         self._pos_hi = 0  # upper bound of every sequence's position (the C side keeps the same count for eager calls)
         self.persistent = bool(self.lib.onebit_decoder_is_persistent(self._handle))
+
+    def _enable_p2p_allreduce(self, tp_group):
+        """One-shot all-reduce over NVLink peer memory (csrc/p2p_allreduce.cu) instead of NCCL: a symmetric buffer per rank
+        (torch symmetric memory maps every peer's buffer into this process), filled with the "not written" pattern -0.0f.
+        Falls back to the NCCL callback, loudly, if symmetric memory cannot be set up on this system."""
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nfloats = 3 * self.tp_size * max(self.max_batch * self.H, 64)
+            buf = symm.empty(nfloats, dtype=torch.float32, device=self.device)
+            buf.fill_(-0.0)
+            hdl = symm.rendezvous(buf, tp_group)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=tp_group)
+            ptrs = (ctypes.c_void_p * self.tp_size)(*[int(p) for p in hdl.buffer_ptrs])
+            rc = self.lib.onebit_decoder_enable_p2p_allreduce(self._handle, self.tp_rank, self.tp_size, ptrs, nfloats * 4)
+            _lib.check(rc, "onebit_decoder_enable_p2p_allreduce")
+            self._symm = (buf, hdl)
+            self.tp_allreduce = "p2p"
+        except Exception as exc:
+            print(f"onebit_b200: one-shot NVLink all-reduce unavailable ({type(exc).__name__}: {exc}); using NCCL", flush=True)
 
     # ------------------------------------------------------------------------------------------
     def close(self):

@@ -19,6 +19,7 @@
 
 #include "fused_gemv.cuh"
 #include "imma_gemv.cuh"
+#include "p2p_allreduce.cuh"
 #include "persist_step.cuh"
 
 namespace onebit {
@@ -577,6 +578,10 @@ struct onebit_decoder {
     float *red_o = nullptr, *red_d = nullptr;  // [max_batch][2]
     // persistent single-kernel step (persist_step.cu): batch <= 2, no tensor parallelism
     PersistState* persist = nullptr;
+    // one-shot all-reduce over NVLink peer memory (p2p_allreduce.cu); enabled by onebit_decoder_enable_p2p_allreduce
+    bool p2p_on = false;
+    P2PComm p2p = {};
+    unsigned* p2p_state = nullptr;  // call counter, CTA ticket, error flag, last counts
     // host-side upper bound of every sequence's position (reset value + steps enqueued): a step that could write past
     // max_seq_len is refused instead of overrunning the KV cache
     int pos_hi = 0;
@@ -688,6 +693,7 @@ int fused_launch(fused::Args a, int param_dtype, cudaStream_t s, int* ctas_per_p
 
 int allreduce(const onebit_decoder* D, float* data, int64_t count, cudaStream_t s) {
     if (D->tp <= 1) return ONEBIT_OK;
+    if (D->p2p_on) return p2p_allreduce(D->p2p, data, count, s);
     if (!D->allreduce) return fail(ONEBIT_ERR_INVALID_ARGUMENT, "tensor-parallel decoder without an all-reduce callback");
     const int rc = D->allreduce(D->allreduce_user, data, count, s);
     return rc == 0 ? ONEBIT_OK : fail(ONEBIT_ERR_CUDA, "all-reduce callback failed with code " + std::to_string(rc));
@@ -912,6 +918,7 @@ extern "C" {
 void onebit_decoder_destroy(onebit_decoder* D) {
     if (!D) return;
     persist_destroy(D->persist);
+    cudaFree(D->p2p_state);
     cudaFree(D->arena);
     delete D;
 }
@@ -1299,9 +1306,37 @@ int onebit_decoder_step_host(onebit_decoder* D, int batch, const int64_t* ids_ho
     return ONEBIT_OK;
 }
 
+int onebit_decoder_enable_p2p_allreduce(onebit_decoder* D, int rank, int nranks, void* const* peer_buffers, size_t buffer_bytes) {
+    ONEBIT_REQUIRE(D && peer_buffers && D->tp > 1 && nranks == D->tp && rank >= 0 && rank < nranks && nranks <= kP2PMaxRanks,
+                   "decoder_enable_p2p_allreduce: bad arguments (needs a tensor-parallel decoder, nranks == tp_size <= 8)");
+    const size_t cap = buffer_bytes / sizeof(float) / (3 * (size_t)nranks);
+    const size_t need = (size_t)D->cfg.max_batch * D->cfg.hidden_size;
+    ONEBIT_REQUIRE(cap >= need, "decoder_enable_p2p_allreduce: symmetric buffer too small (needs 3 * nranks * max_batch * hidden floats)");
+    if (!D->p2p_state) {
+        ONEBIT_CUDA_TRY(cudaMalloc(&D->p2p_state, 8 * sizeof(unsigned)));
+        ONEBIT_CUDA_TRY(cudaMemset(D->p2p_state, 0, 8 * sizeof(unsigned)));
+    }
+    P2PComm c = {};
+    c.rank = rank; c.n = nranks; c.cap = cap;
+    for (int r = 0; r < nranks; ++r) {
+        ONEBIT_REQUIRE(peer_buffers[r] != nullptr, "decoder_enable_p2p_allreduce: NULL peer buffer");
+        c.peer[r] = static_cast<float*>(peer_buffers[r]);
+    }
+    c.call_counter = D->p2p_state; c.cta_ticket = D->p2p_state + 1; c.error_flag = reinterpret_cast<int*>(D->p2p_state + 2);
+    c.last_count = D->p2p_state + 4;
+    D->p2p = c;
+    D->p2p_on = true;
+    return ONEBIT_OK;
+}
+
 int onebit_decoder_status(onebit_decoder* D, int* code) {
     ONEBIT_REQUIRE(D && code, "decoder_status: bad arguments");
     *code = 0;
+    if (D->p2p_on) {  // 3 = a peer's data did not arrive in the one-shot all-reduce
+        int e = 0;
+        ONEBIT_CUDA_TRY(cudaMemcpy(&e, D->p2p.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) { *code = 3; return ONEBIT_OK; }
+    }
     if (D->persist) return persist_abort_flag(D->persist, code);
     return ONEBIT_OK;
 }

@@ -28,7 +28,8 @@ for graph in (False, True):
         print(f"tp_check: tiny model, graph={graph}", flush=True)
     dec = BitLlamaDecoderB200(config, sd, device=dev, max_seq_len=64, max_batch=2, param_dtype=torch.float32,
                               use_graph=graph, tp_group=dist.group.WORLD)
-    print(f"tp_check[{rank}]: decoder created (launch path: fused stages, tp={world})", flush=True)
+    print(f"tp_check[{rank}]: decoder created (launch path: fused stages, tp={world}, all-reduce: {dec.tp_allreduce})", flush=True)
+    res["allreduce"] = dec.tp_allreduce
     dec.reset(ids[:, 0])
     torch.cuda.synchronize()
     print(f"tp_check[{rank}]: warm-up steps done", flush=True)
@@ -38,7 +39,7 @@ for graph in (False, True):
     dec.close()
     dec._graphs.clear()  # captured NCCL kernels must be gone before the process group is torn down
     del dec
-ok = all(v < 2e-3 for v in res.values())
+ok = all(v < 2e-3 for k, v in res.items() if k != 'allreduce')
 if rank == 0:
     print(json.dumps({"tp": world, "tiny_model_logits_rel_l2": res, "parity_ok": ok}), flush=True)
 def finish(code):
@@ -69,5 +70,6 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 64
 if rank == 0:
     print(json.dumps({"tp": world, "model": os.environ.get("ONEBIT_TP_MODEL", "7b"), "tiny_model_logits_rel_l2": res, "parity_ok": ok,
-                      "tp_ms_per_step": ms, "tp_tok_s": 1e3 / ms, "launches_per_step": dec.launches_per_step()}), flush=True)
+                      "tp_ms_per_step": ms, "tp_tok_s": 1e3 / ms, "launches_per_step": dec.launches_per_step(),
+                      "allreduce": dec.tp_allreduce, "status": dec.status()}), flush=True)
 finish(0 if ok else 1)
