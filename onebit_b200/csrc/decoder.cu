@@ -1076,9 +1076,11 @@ int onebit_decoder_step(onebit_decoder* D, int batch, const int64_t* forced_ids_
     }
     // Tensor-parallel steps interleave NCCL kernels (another stream, event-ordered): keep plain stream order there, so
     // that no early-launched CTA of ours can sit on an SM waiting for a collective that needs that SM.
-    if (D->tp > 1) pdl_suspend(true);
+    // (with the one-shot peer-memory all-reduce every kernel of the step is ours: programmatic dependent launch stays on)
+    const bool suspend = D->tp > 1 && !D->p2p_on;
+    if (suspend) pdl_suspend(true);
     const int rc = decoder_step_impl(D, batch, forced_ids_dev, logits_dev, stream);
-    if (D->tp > 1) pdl_suspend(false);
+    if (suspend) pdl_suspend(false);
     return rc;
 }
 
