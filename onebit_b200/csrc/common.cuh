@@ -89,8 +89,9 @@ struct Tc5LaunchProblem {
     const int8_t* w;    // [N][K/8]
     const __half* h16;  // [K] input_factor as fp16
     const void* g;      // [N] weight_scale (param dtype) or nullptr
-    float* t;           // [ksplit][M][N]
+    float* t;           // [ksplit][M][ldt]
     int N;
+    int ldt;            // leading dimension of t; 0 = N
 };
 struct Tc5Launch {
     const __half* x16;  // [M][K]

@@ -44,6 +44,7 @@ enum GlueMode {
 struct GlueArgs {
     int mode, M, K, nprob, write_x_f16;
     int stats_from_data;  // RESID_NORM: t_a was all-reduced across ranks -> (sum, sumsq) from the data itself
+    int n_ln;             // LayerNorm denominator of the producer(s) when it is not K (tensor-parallel shards); 0 = K
     const float* t_a; const float* stats_a; int ncta_a;   // previous GEMV output (already * g), [ncta][M][2] partials
     const float* t_b; const float* stats_b; int ncta_b;
     const float* resid_in; float* resid_out;              // [M][K] fp32
@@ -174,8 +175,9 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
     float mean_a = 0.f, rstd_a = 1.f, mean_b = 0.f, rstd_b = 1.f;
     if (A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL) {
         block_reduce_sum<4>(st, shd);
-        finish_ln(st[0], st[1], K, A.ln_eps, mean_a, rstd_a);
-        if (A.mode == GLUE_SILU_MUL) finish_ln(st[2], st[3], K, A.ln_eps, mean_b, rstd_b);
+        const int n_ln = A.n_ln > 0 ? A.n_ln : K;
+        finish_ln(st[0], st[1], n_ln, A.ln_eps, mean_a, rstd_a);
+        if (A.mode == GLUE_SILU_MUL) finish_ln(st[2], st[3], n_ln, A.ln_eps, mean_b, rstd_b);
     }
     // ---- x
     if (norm_mode) {
@@ -814,6 +816,9 @@ int tc5_ksplit(int row_tiles, int K, int ksplit_max) {
 int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int* cur_io, bool only_proj = false) {
     const onebit_decoder_config& C = D->cfg;
     const int H = C.hidden_size, I = C.intermediate_size, pd = C.param_dtype, B = C.max_batch;
+    // tensor parallelism (Megatron layout, tp.py): q/k/v and gate/up hold Hl / Il of the rows, o / down a K slice of Hk / Ik
+    // columns (zero padded); 4 small all-reduces per layer as on the fused path
+    const int Hl = D->Hl, Hk = D->Hk, Il = D->Il, Ik = D->Ik, tp = D->tp;
     int cur = *cur_io, rc;
     auto reduce = [&](float* t0, float* t1, float* t2, int n, int nprob, int S, float* stats) -> int {
         if (only_proj) return ONEBIT_OK;
@@ -829,83 +834,87 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         GlueArgs g = {};
         g.mode = l == 0 ? GLUE_EMBED_NORM : GLUE_RESID_NORM;
         g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
-        g.t_a = D->t_d; g.stats_a = D->red_d; g.ncta_a = kReduceSlices;
+        g.t_a = D->t_d; g.stats_a = D->red_d; g.ncta_a = kReduceSlices; g.stats_from_data = tp > 1;
         g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1];
         g.embed = D->embed; g.ids = D->ids; g.ln_w = P.input_layernorm; g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
         if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
         cur ^= 1;
-        // ---- q, k, v
+        // ---- q, k, v (column-parallel: local rows)
         Tc5Launch t = {};
         t.x16 = D->x_f16; t.M = M; t.K = H; t.nprob = 3; t.param_dtype = pd;
-        t.ksplit = tc5_ksplit(3 * ((H + 127) / 128), H, D->ksplit_max);
+        t.ksplit = tc5_ksplit(3 * ((Hl + 127) / 128), H, D->ksplit_max);
         const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
         float* tq[3];
         for (int i = 0; i < 3; ++i) {
             tq[i] = D->t_qkv + (size_t)i * B * H * D->ksplit_max;
             t.p[i].w = static_cast<const int8_t*>(qkv[i]->weight); t.p[i].h16 = h16[i]; t.p[i].g = qkv[i]->weight_scale;
-            t.p[i].t = tq[i]; t.p[i].N = H;
+            t.p[i].t = tq[i]; t.p[i].N = Hl;
         }
         rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
-        rc = reduce(tq[0], tq[1], tq[2], H, 3, t.ksplit, D->red_qkv); if (rc) return rc;
-        // ---- attention
+        rc = reduce(tq[0], tq[1], tq[2], Hl, 3, t.ksplit, D->red_qkv); if (rc) return rc;
+        if (!only_proj) { rc = allreduce(D, D->red_qkv, (int64_t)3 * kReduceSlices * M * 2, s); if (rc) return rc; }
+        // ---- attention over the local heads
         AttnArgs at = {};
         at.t_q = tq[0]; at.t_k = tq[1]; at.t_v = tq[2];
         const size_t pstride = (size_t)kReduceSlices * M * 2;  // statistics of one projection: kReduceSlices partial records
         at.stats_q = D->red_qkv; at.stats_k = D->red_qkv + pstride; at.stats_v = D->red_qkv + 2 * pstride; at.ncta = kReduceSlices;
-        at.M = M; at.H = H; at.n_ln = H; at.out_ld = H; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len; at.pos = D->pos;
+        at.M = M; at.H = Hl; at.n_ln = H; at.out_ld = Hk; at.n_heads = D->heads_l; at.max_seq = C.max_seq_len; at.pos = D->pos;
         at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
         const size_t layer_cache = (size_t)B * D->heads_l * C.max_seq_len * kHeadDim;
         at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
         // many (sequence, head) CTAs: stream the cached rows from L2 instead of staging them (several CTAs per SM)
         at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = 0;
         if (!only_proj) {
-            rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), (size_t)std::max(C.max_seq_len, 4 * kHeadDim) * sizeof(float), s, at);
+            rc = launch_pdl(attn_kernel, dim3(M, D->heads_l), dim3(kHeadDim), (size_t)std::max(C.max_seq_len, 4 * kHeadDim) * sizeof(float), s, at);
             if (rc) return rc; ++*launches;
         }
-        // ---- glue 2: attention output -> fp16
+        // ---- glue 2: attention output [M][Hk] (pad columns stay zero) -> fp16
         g = {};
-        g.mode = GLUE_PLAIN; g.M = M; g.K = H; g.nprob = 1; g.x_plain = D->attn_out; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
+        g.mode = GLUE_PLAIN; g.M = M; g.K = Hk; g.nprob = 1; g.x_plain = D->attn_out; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
         if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
-        // ---- o_proj
+        // ---- o_proj (row-parallel: K slice) + all-reduce of the partial sums
         t = {};
-        t.x16 = D->x_f16; t.M = M; t.K = H; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, H, D->ksplit_max);
+        t.x16 = D->x_f16; t.M = M; t.K = Hk; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, Hk, D->ksplit_max);
         t.p[0].w = static_cast<const int8_t*>(P.o.weight); t.p[0].h16 = h16[3]; t.p[0].g = P.o.weight_scale; t.p[0].t = D->t_o; t.p[0].N = H;
         rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
         rc = reduce(D->t_o, nullptr, nullptr, H, 1, t.ksplit, D->red_o); if (rc) return rc;
-        // ---- glue 3: resid + LN(o) -> RMSNorm -> fp16 x
+        if (!only_proj) { rc = allreduce(D, D->t_o, (int64_t)M * H, s); if (rc) return rc; }
+        // ---- glue 3: resid + LN(o) -> RMSNorm -> fp16 x (statistics from the all-reduced data under tensor parallelism)
         g = {};
         g.mode = GLUE_RESID_NORM; g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
-        g.t_a = D->t_o; g.stats_a = D->red_o; g.ncta_a = kReduceSlices;
+        g.t_a = D->t_o; g.stats_a = D->red_o; g.ncta_a = kReduceSlices; g.stats_from_data = tp > 1;
         g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = P.post_attention_layernorm;
         g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
         if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
         cur ^= 1;
-        // ---- gate, up
+        // ---- gate, up (column-parallel); outputs laid out with the padded width the down_proj shard consumes
         t = {};
         t.x16 = D->x_f16; t.M = M; t.K = H; t.nprob = 2; t.param_dtype = pd;
-        t.ksplit = tc5_ksplit(2 * ((I + 127) / 128), H, D->ksplit_max);
+        t.ksplit = tc5_ksplit(2 * ((Il + 127) / 128), H, D->ksplit_max);
         const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
         float* tg[2];
         for (int i = 0; i < 2; ++i) {
             tg[i] = D->t_gu + (size_t)i * B * I * D->ksplit_max;
             t.p[i].w = static_cast<const int8_t*>(gu[i]->weight); t.p[i].h16 = h16[4 + i]; t.p[i].g = gu[i]->weight_scale;
-            t.p[i].t = tg[i]; t.p[i].N = I;
+            t.p[i].t = tg[i]; t.p[i].N = Il; t.p[i].ldt = Ik;
         }
         rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
-        rc = reduce(tg[0], tg[1], nullptr, I, 2, t.ksplit, D->red_gu); if (rc) return rc;
-        // ---- glue 4: silu(LN(gate)) * LN(up) -> fp16 [M][I]
+        rc = reduce(tg[0], tg[1], nullptr, Ik, 2, t.ksplit, D->red_gu); if (rc) return rc;
+        if (!only_proj) { rc = allreduce(D, D->red_gu, (int64_t)2 * kReduceSlices * M * 2, s); if (rc) return rc; }
+        // ---- glue 4: silu(LN(gate)) * LN(up) -> fp16 [M][Ik]
         g = {};
-        g.mode = GLUE_SILU_MUL; g.M = M; g.K = I; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->xI_f16;
+        g.mode = GLUE_SILU_MUL; g.M = M; g.K = Ik; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->xI_f16; g.n_ln = I;
         g.t_a = tg[0]; g.stats_a = D->red_gu; g.ncta_a = kReduceSlices;
         g.t_b = tg[1]; g.stats_b = D->red_gu + (size_t)kReduceSlices * M * 2; g.ncta_b = kReduceSlices;
         g.ln_eps = C.ln_eps;
         if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
-        // ---- down_proj
+        // ---- down_proj (row-parallel) + all-reduce of the partial sums
         t = {};
-        t.x16 = D->xI_f16; t.M = M; t.K = I; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, I, D->ksplit_max);
+        t.x16 = D->xI_f16; t.M = M; t.K = Ik; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, Ik, D->ksplit_max);
         t.p[0].w = static_cast<const int8_t*>(P.down.weight); t.p[0].h16 = h16[6]; t.p[0].g = P.down.weight_scale; t.p[0].t = D->t_d; t.p[0].N = H;
         rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
         rc = reduce(D->t_d, nullptr, nullptr, H, 1, t.ksplit, D->red_d); if (rc) return rc;
+        if (!only_proj) { rc = allreduce(D, D->t_d, (int64_t)M * H, s); if (rc) return rc; }
     }
     *cur_io = cur;
     return ONEBIT_OK;
@@ -967,7 +976,7 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const bool big = B > 4 && tp == 1;  // batches the bit-plane GEMV cannot hold: tcgen05 path with split-K partials
+    const bool big = B > 4;  // batches the bit-plane GEMV cannot hold: tcgen05 path with split-K partials
     const size_t ks = big ? kKSplitMax : 1;
     D->ksplit_max = (int)ks;
     const size_t o_res0 = take((size_t)B * H * 4), o_res1 = take((size_t)B * H * 4);
@@ -985,9 +994,9 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     const size_t o_x16 = take((size_t)B * H * 2), o_ids = take(B * 8), o_ids2 = take(B * 8), o_pos = take(B * 4);
     const size_t o_rq = take((size_t)3 * kReduceSlices * B * 2 * 4), o_rg = take((size_t)2 * kReduceSlices * B * 2 * 4);
     const size_t o_ro = take((size_t)kReduceSlices * B * 2 * 4), o_rd = take((size_t)kReduceSlices * B * 2 * 4);
-    const size_t o_xI = take(big ? (size_t)B * I * 2 : 16);
+    const size_t o_xI = take(big ? (size_t)B * std::max(I, D->Ik) * 2 : 16);
     const bool need_h16 = big && cfg->param_dtype != ONEBIT_F16;
-    const size_t o_h16 = take(need_h16 ? (size_t)L * (6 * (size_t)H + I) * 2 : 16);
+    const size_t o_h16 = take(need_h16 ? (size_t)L * (5 * (size_t)H + D->Hk + D->Ik) * 2 : 16);
     cudaError_t e = cudaMalloc(&D->arena, off);
     if (e != cudaSuccess) {
         delete D;
@@ -1014,7 +1023,7 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
         for (int l = 0; l < L; ++l) {
             const onebit_bitlinear_params* bl[7] = {&layers[l].q, &layers[l].k, &layers[l].v, &layers[l].o, &layers[l].gate, &layers[l].up, &layers[l].down};
             for (int i = 0; i < 7; ++i) {
-                const int k = i == 6 ? I : H;
+                const int k = i == 6 ? D->Ik : (i == 3 ? D->Hk : H);  // local K of the shard (padded for o / down)
                 if (need_h16) {
                     const int rc = launch_to_half(bl[i]->input_factor, hp, k, cfg->param_dtype, nullptr);
                     if (rc != ONEBIT_OK) { onebit_decoder_destroy(D); return rc; }
@@ -1120,7 +1129,7 @@ static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced
         if (rc) return rc;
     }
     if (!use_fused && D->tp > 1)
-        return fail(ONEBIT_ERR_INVALID_ARGUMENT, "tensor-parallel decode needs the fused stages (batch <= 2, ONEBIT_FUSED != 0)");
+        return fail(ONEBIT_ERR_INVALID_ARGUMENT, "tensor-parallel decode needs the fused stages (batch <= 2, ONEBIT_FUSED != 0) or a decoder created with max_batch > 4 (batched tcgen05 path)");
     for (int l = 0; !use_fused && l < C.num_layers; ++l) {
         const onebit_layer_params& P = D->layers[l];
         // ---- glue 1: (embed | resid + LN(down of previous layer)) -> RMSNorm -> q/k/v digits

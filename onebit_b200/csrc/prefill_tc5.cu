@@ -117,6 +117,7 @@ struct Tc5Problem {
     const void* g;      // [N] TP weight_scale or nullptr
     float* t;           // [ksplit][M][N] fp32 (split z writes its partial sums at t + z * M * N)
     int N, tile_begin;  // rows; first row tile (blockIdx.x) of this problem
+    int ldt;            // leading dimension of t (>= N; padded K of a row-parallel consumer under tensor parallelism)
 };
 struct PrefillArgs {
     Tc5Problem p[kMaxProblems];
@@ -155,7 +156,7 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     const int c_begin = 2 * (int)(((long long)half_all * blockIdx.z) / A.ksplit);
     const int c_end = (int)blockIdx.z + 1 == A.ksplit ? nchunks_all : 2 * (int)(((long long)half_all * (blockIdx.z + 1)) / A.ksplit);
     const int nchunks = c_end - c_begin;
-    float* tout = P.t + (size_t)blockIdx.z * A.M * P.N;
+    float* tout = P.t + (size_t)blockIdx.z * A.M * P.ldt;
     const int m_valid = min(kTileM, A.M - m0);
     const int umma_n = max(16, (m_valid + 15) & ~15);  // tokens covered by the MMA (multiple of 16)
 
@@ -338,7 +339,7 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int m = m0 + cb + j;
-                        if (m < A.M) tout[(size_t)m * P.N + n] = __uint_as_float(v[j]) * gs;
+                        if (m < A.M) tout[(size_t)m * P.ldt + n] = __uint_as_float(v[j]) * gs;
                     }
                 }
             }
@@ -484,7 +485,7 @@ int launch_tc5(const Tc5Launch& L, cudaStream_t s) {
     int tiles = 0;
     for (int i = 0; i < L.nprob; ++i) {
         a.p[i].w = reinterpret_cast<const uint8_t*>(L.p[i].w); a.p[i].h = L.p[i].h16; a.p[i].g = L.p[i].g; a.p[i].t = L.p[i].t;
-        a.p[i].N = L.p[i].N; a.p[i].tile_begin = tiles;
+        a.p[i].N = L.p[i].N; a.p[i].tile_begin = tiles; a.p[i].ldt = L.p[i].ldt > 0 ? L.p[i].ldt : L.p[i].N;
         tiles += (L.p[i].N + tile_n - 1) / tile_n;
         if (!aligned16(L.p[i].w)) a.wtma = 0;
     }
@@ -514,7 +515,7 @@ int launch_dense_tc5(const __half* x16, const __half* w16, float* out, int64_t m
     if (rc) return rc;
     PrefillArgs a = {};
     a.nprob = 1; a.M = (int)m; a.K = (int)k; a.ksplit = 1;
-    a.p[0].t = out; a.p[0].N = (int)n; a.p[0].tile_begin = 0;
+    a.p[0].t = out; a.p[0].N = (int)n; a.p[0].tile_begin = 0; a.p[0].ldt = (int)n;
     dim3 grid((unsigned)((n + 127) / 128), 1, 1);
     const CUtensorMap wm[3] = {amap, xmap, xmap};
     return launch_inst<__half, 1, 64, true>(xmap, wm, a, grid, s);

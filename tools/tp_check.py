@@ -39,7 +39,15 @@ for graph in (False, True):
     dec.close()
     dec._graphs.clear()  # captured NCCL kernels must be gone before the process group is torn down
     del dec
-ok = all(v < 2e-3 for k, v in res.items() if k != 'allreduce')
+# batched decode (tcgen05 path) under tensor parallelism: 8 sequences = the fixture's two, four times over
+ids8 = torch.cat([ids, ids.flip(0), ids, ids.flip(0)], dim=0)
+want8 = np.concatenate([z["logits"][:, :24], z["logits"][::-1, :24], z["logits"][:, :24], z["logits"][::-1, :24]], axis=0)
+dec = BitLlamaDecoderB200(config, sd, device=dev, max_seq_len=64, max_batch=8, param_dtype=torch.float16, tp_group=dist.group.WORLD)
+got8 = dec.forward_tokens(ids8).cpu().numpy()
+res["batched8_f16"] = oracle.rel_l2(got8, want8)
+dec.close(); dec._graphs.clear(); del dec
+print(f"tp_check[{rank}]: batched tensor-parallel pass done", flush=True)
+ok = all(v < 3e-3 for k, v in res.items() if k != 'allreduce')
 if rank == 0:
     print(json.dumps({"tp": world, "tiny_model_logits_rel_l2": res, "parity_ok": ok}), flush=True)
 def finish(code):
@@ -56,9 +64,10 @@ if os.environ.get("ONEBIT_TP_TIMING", "0") != "1":
 # timing at LLaMA-7B / LLaMA2-13B widths (ONEBIT_TP_TIMING=1, ONEBIT_TP_MODEL=7b|13b)
 from onebit_b200 import LLAMA2_13B
 cfg7 = dict(LLAMA2_13B if os.environ.get("ONEBIT_TP_MODEL", "7b") == "13b" else LLAMA_7B)
-dec = BitLlamaDecoderB200(cfg7, synthetic_state_dict(cfg7, seed=0), device=dev, max_seq_len=256, max_batch=1,
+TB = int(os.environ.get("ONEBIT_TP_BATCH", "1"))
+dec = BitLlamaDecoderB200(cfg7, synthetic_state_dict(cfg7, seed=0), device=dev, max_seq_len=256, max_batch=TB,
                           tp_group=dist.group.WORLD)
-dec.reset(torch.tensor([5]))
+dec.reset(torch.full((TB,), 5))
 for _ in range(8):
     dec.step()
 torch.cuda.synchronize(); dist.barrier()
@@ -70,6 +79,6 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 64
 if rank == 0:
     print(json.dumps({"tp": world, "model": os.environ.get("ONEBIT_TP_MODEL", "7b"), "tiny_model_logits_rel_l2": res, "parity_ok": ok,
-                      "tp_ms_per_step": ms, "tp_tok_s": 1e3 / ms, "launches_per_step": dec.launches_per_step(),
+                      "batch": TB, "tp_ms_per_step": ms, "tp_tok_s": TB * 1e3 / ms, "launches_per_step": dec.launches_per_step(),
                       "allreduce": dec.tp_allreduce, "status": dec.status()}), flush=True)
 finish(0 if ok else 1)
