@@ -181,6 +181,15 @@ ONEBIT_API int onebit_decoder_kernel_launches_per_step(onebit_decoder* dec);
 /* Persistent single-kernel step (experimental, opt-in with ONEBIT_PERSIST=1; batch <= 2, tp_size == 1): 1 if this
  * decoder uses it. */
 ONEBIT_API int onebit_decoder_is_persistent(onebit_decoder* dec);
+/* Prompt pass (replaces the q_len > 1 forward of BitLlamaForCausalLMInf, modeling_bitllama.py:1217-1315,1546-1611, with the
+ * causal mask of :1267-1269): all T tokens of `batch` sequences at once — every BitLinear is one tcgen05 GEMM over
+ * batch * T tokens, attention a causal flash kernel; K / V are written to the static cache at positions pos0 .. pos0+T-1.
+ * ids_dev: device int64 [batch][T]. logits_last_dev: device fp32 [batch][V] or NULL. logits_all_dev: device fp32
+ * [batch*T][V] or NULL. Afterwards the decoder's next ids are each prompt's greedy continuation and its positions
+ * pos0 + T, so onebit_decoder_step continues the sequences. Single-GPU decoders only. Not CUDA-graph capturable (it
+ * sizes and may allocate its workspace). */
+ONEBIT_API int onebit_decoder_prefill(onebit_decoder* dec, int batch, int T, int pos0, const int64_t* ids_dev,
+                                       float* logits_last_dev, float* logits_all_dev, void* stream);
 /* Tensor parallelism without a library collective: switch the decoder's all-reduces (partial sums of o_proj / down_proj,
  * LayerNorm statistics of q/k/v and gate/up — SURVEY.md 8e; the reference has no tensor parallelism for BitLinearInf) from the
  * callback to a one-shot Lamport all-reduce over NVLink peer memory. peer_buffers[r] = rank r's symmetric buffer of

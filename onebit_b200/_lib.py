@@ -51,6 +51,7 @@ SIGNATURES = {
     "onebit_decoder_positions": (_vp, [_vp]),
     "onebit_decoder_kernel_launches_per_step": (_int, [_vp]),
     "onebit_decoder_is_persistent": (_int, [_vp]),
+    "onebit_decoder_prefill": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "onebit_decoder_enable_p2p_allreduce": (_int, [_vp, _int, _int, _vp, _sz]),
     "onebit_decoder_status": (_int, [_vp, _c.POINTER(_int)]),
     "onebit_decoder_read_trace": (_int, [_vp, _vp, _int]),

@@ -254,6 +254,35 @@ class BitLlamaDecoderB200:
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
+    def prefill(self, input_ids: torch.Tensor, all_logits: bool = False, pos0: int = 0) -> torch.Tensor:
+        """Prompt pass over [B, T] token ids in ONE go (the reference's q_len > 1 forward, modeling_bitllama.py:1217-1315):
+        every BitLinear is a tcgen05 GEMM over B*T tokens, attention is causal flash attention, K/V go to the static
+        cache. Returns the last-token logits [B, V] (or all logits [B, T, V] with `all_logits`); afterwards `step()` /
+        `next_ids()` continue the sequences (next ids = greedy continuation of each prompt)."""
+        if self.tp_size > 1:
+            raise RuntimeError("onebit_b200: prefill() is single-GPU; tensor-parallel decoders feed the prompt with step()")
+        input_ids = torch.as_tensor(input_ids, dtype=torch.int64)
+        b, t = input_ids.shape
+        if b > self.max_batch or pos0 + t > self.max_seq_len:
+            raise RuntimeError(f"onebit_b200: prompt [{b}, {t}] at position {pos0} does not fit max_batch={self.max_batch}, "
+                               f"max_seq_len={self.max_seq_len}")
+        if int(input_ids.min()) < 0 or int(input_ids.max()) >= self.V:
+            raise RuntimeError(f"onebit_b200: token ids must lie in [0, vocab_size={self.V})")
+        if b not in self._warmed:
+            self.reset(input_ids[:, 0])  # eager warm-up steps of the decode kernels (they must not load inside a graph capture)
+        ids_dev = input_ids.to(self.device).contiguous()
+        last = torch.empty((b, self.V), dtype=torch.float32, device=self.device)
+        full = torch.empty((b * t, self.V), dtype=torch.float32, device=self.device) if all_logits else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.onebit_decoder_prefill(self._handle, b, t, int(pos0), ids_dev.data_ptr(), last.data_ptr(),
+                                                 full.data_ptr() if full is not None else None, self._stream())
+        _lib.check(rc, "onebit_decoder_prefill")
+        self.batch = b
+        self._pos_hi = pos0 + t
+        self.logits[:b].copy_(last)
+        return full.view(b, t, self.V) if all_logits else last
+
+    @torch.no_grad()
     def forward_tokens(self, input_ids: torch.Tensor) -> torch.Tensor:
         """Teacher-forced pass over [B, T] token ids through the decode path; returns logits [B, T, V] (fp32) —
         the quantity BitLlamaForCausalLMInf.forward returns (:1546-1611), computed one position at a time."""
@@ -270,26 +299,29 @@ class BitLlamaDecoderB200:
         return out
 
     @torch.no_grad()
-    def generate(self, prompt_ids: torch.Tensor, max_new_tokens: int) -> torch.Tensor:
+    def generate(self, prompt_ids: torch.Tensor, max_new_tokens: int, use_prefill: bool = False) -> torch.Tensor:
         """Greedy decoding (generation/utils.py:2491-2571 with do_sample=False, no EOS stop): returns
         [B, T0 + max_new_tokens] like `model.generate`."""
         prompt_ids = torch.as_tensor(prompt_ids, dtype=torch.int64)
         b, t0 = prompt_ids.shape
         if t0 + max_new_tokens - 1 > self.max_seq_len:
             raise RuntimeError(f"onebit_b200: prompt {t0} + {max_new_tokens} new tokens do not fit max_seq_len={self.max_seq_len}")
-        self.reset(prompt_ids[:, 0])
         ids_dev = prompt_ids.to(self.device)
-        for i in range(t0):
-            self.step(ids_dev[:, i])
+        if use_prefill:  # the whole prompt in one pass (tcgen05 GEMMs + causal flash attention), then decode steps
+            self.prefill(prompt_ids)
+        else:
+            self.reset(prompt_ids[:, 0])
+            for i in range(t0):
+                self.step(ids_dev[:, i])
         new = [self.next_ids().clone()]
         for _ in range(max_new_tokens - 1):
             self.step()
             new.append(self.next_ids().clone())
         return torch.cat([ids_dev, torch.stack(new, dim=1)], dim=1)
 
-    def perplexity(self, input_ids: torch.Tensor) -> float:
+    def perplexity(self, input_ids: torch.Tensor, use_prefill: bool = False) -> float:
         """evaluation/lm_eval.py:99-124: per window CE(mean over shifted tokens) * seqlen, exp(sum / (n * seqlen))."""
-        logits = self.forward_tokens(input_ids)
+        logits = self.prefill(input_ids, all_logits=True) if use_prefill else self.forward_tokens(input_ids)
         b, t, _ = logits.shape
         ids = torch.as_tensor(input_ids).to(self.device)
         nll = 0.0

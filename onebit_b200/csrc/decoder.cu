@@ -20,6 +20,7 @@
 #include "fused_gemv.cuh"
 #include "imma_gemv.cuh"
 #include "p2p_allreduce.cuh"
+#include "prefill_attn.cuh"
 #include "persist_step.cuh"
 
 namespace onebit {
@@ -525,6 +526,17 @@ __global__ void __launch_bounds__(256) tc5_reduce_stats_kernel(const __grid_cons
         *reinterpret_cast<float2*>(A.stats + (((size_t)p * kReduceSlices + z) * A.M + m) * 2) = make_float2((float)st[0], (float)st[1]);
 }
 
+// prompt pass helpers: last-token rows of the normalised stream -> [B][H] for lm_head; positions for the decode steps after
+__global__ void gather_last_rows_kernel(const __half* __restrict__ x, __half* __restrict__ out, int T, int H) {
+    const int b = blockIdx.x;
+    const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * T + T - 1) * H);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)b * H);
+    for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];
+}
+__global__ void set_positions_kernel(int* pos, int value, int n) {
+    if ((int)threadIdx.x < n) pos[threadIdx.x] = value;
+}
+
 template <typename... KArgs, typename... Args>
 int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -580,6 +592,11 @@ struct onebit_decoder {
     float *red_o = nullptr, *red_d = nullptr;  // [max_batch][2]
     // persistent single-kernel step (persist_step.cu): batch <= 2, no tensor parallelism
     PersistState* persist = nullptr;
+    // prompt pass (onebit_decoder_prefill): workspace for `pf_cap` tokens, allocated on first use
+    char* pf_ws = nullptr;
+    size_t pf_cap = 0;
+    std::vector<const __half*> pf_h16;  // fp16 input_factor copies (shared with the batched decode path when it has them)
+    __half* pf_h16_store = nullptr;
     // one-shot all-reduce over NVLink peer memory (p2p_allreduce.cu); enabled by onebit_decoder_enable_p2p_allreduce
     bool p2p_on = false;
     P2PComm p2p = {};
@@ -928,6 +945,8 @@ void onebit_decoder_destroy(onebit_decoder* D) {
     if (!D) return;
     persist_destroy(D->persist);
     cudaFree(D->p2p_state);
+    cudaFree(D->pf_ws);
+    cudaFree(D->pf_h16_store);
     cudaFree(D->arena);
     delete D;
 }
@@ -1249,6 +1268,183 @@ static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced
 
 // Enqueue only the BitLinear GEMV launches of one step (4 per layer), reusing whatever activation digits are
 // resident: the weight-streaming kernel chain on its own, for the roofline measurement in bench.py.
+// Prompt pass: all T tokens of `batch` sequences at once (what the reference's forward does for q_len > 1,
+// modeling_bitllama.py:1217-1315,1546-1611; lm_eval.py:99-124 runs 2048-token windows this way). Every BitLinear is one
+// tcgen05 GEMM over M = batch * T tokens (prefill tile for M > 64), attention is the causal flash kernel of prefill_attn.cu,
+// K / V land in the static cache at positions pos0 .. pos0 + T - 1, so decode steps continue from there.
+//   ids_dev            [batch][T] int64 token ids (device)
+//   logits_last_dev    [batch][V] fp32 logits of every sequence's last token, or NULL
+//   logits_all_dev     [batch * T][V] fp32 logits of every token (perplexity / parity), or NULL
+// On return the decoder's next ids are the greedy continuation of each prompt and its positions are pos0 + T.
+int onebit_decoder_prefill(onebit_decoder* D, int batch, int T, int pos0, const int64_t* ids_dev, float* logits_last_dev,
+                           float* logits_all_dev, void* stream) {
+    ONEBIT_REQUIRE(D && ids_dev && batch >= 1 && batch <= D->cfg.max_batch && T >= 1 && pos0 >= 0, "decoder_prefill: bad arguments");
+    ONEBIT_REQUIRE(D->tp == 1, "decoder_prefill: the prompt pass is single-GPU (tensor-parallel decoders feed the prompt step by step)");
+    ONEBIT_REQUIRE(pos0 + T <= D->cfg.max_seq_len, "decoder_prefill: the prompt does not fit max_seq_len");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const onebit_decoder_config& C = D->cfg;
+    const int H = C.hidden_size, I = C.intermediate_size, L = C.num_layers, pd = C.param_dtype, V = C.vocab_size;
+    const size_t M = (size_t)batch * T;
+    ONEBIT_REQUIRE(M < (1u << 30), "decoder_prefill: too many tokens");
+    // ---- workspace
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t b_res = up(M * H * 4), b_tq = up(3 * M * H * 4), b_th = up(M * H * 4), b_tg = up(2 * M * I * 4);
+    const size_t b_xa = up(M * H * 2), b_xi = up(M * I * 2), b_q = up(M * H * 2), b_st = up((size_t)3 * kReduceSlices * M * 2 * 4);
+    const size_t need = 2 * b_res + b_tq + 2 * b_th + b_tg + b_xa + b_xi + b_q + 4 * b_st;
+    if (D->pf_cap < need) {
+        cudaFree(D->pf_ws);
+        D->pf_ws = nullptr;
+        D->pf_cap = 0;
+        cudaError_t e = cudaMalloc(&D->pf_ws, need);
+        if (e != cudaSuccess) return fail(ONEBIT_ERR_CUDA, std::string("decoder_prefill: cudaMalloc of the prompt workspace: ") + cudaGetErrorString(e));
+        D->pf_cap = need;
+    }
+    char* w = D->pf_ws;
+    float* resid[2] = {(float*)w, (float*)(w + b_res)}; w += 2 * b_res;
+    float* t_qkv = (float*)w; w += b_tq;
+    float* t_o = (float*)w; w += b_th;
+    float* t_d = (float*)w; w += b_th;
+    float* t_gu = (float*)w; w += b_tg;
+    __half* xa = (__half*)w; w += b_xa;
+    __half* xi = (__half*)w; w += b_xi;
+    __half* q16 = (__half*)w; w += b_q;
+    float* st_qkv = (float*)w; w += b_st;
+    float* st_o = (float*)w; w += b_st;
+    float* st_gu = (float*)w; w += b_st;
+    float* st_d = (float*)w; w += b_st;
+    // ---- fp16 input_factor vectors (the tcgen05 A operand folds them in)
+    if (D->pf_h16.empty()) {
+        if (!D->h16.empty()) {
+            D->pf_h16 = D->h16;
+        } else {
+            D->pf_h16.resize((size_t)L * 7);
+            __half* hp = nullptr;
+            if (pd != ONEBIT_F16) {
+                ONEBIT_CUDA_TRY(cudaMalloc(&D->pf_h16_store, (size_t)L * (6 * (size_t)H + I) * 2));
+                hp = D->pf_h16_store;
+            }
+            for (int l = 0; l < L; ++l) {
+                const onebit_layer_params& P = D->layers[l];
+                const onebit_bitlinear_params* bl[7] = {&P.q, &P.k, &P.v, &P.o, &P.gate, &P.up, &P.down};
+                for (int i = 0; i < 7; ++i) {
+                    const int k = i == 6 ? I : H;
+                    if (pd != ONEBIT_F16) {
+                        const int rc = launch_to_half(bl[i]->input_factor, hp, k, pd, s);
+                        if (rc) return rc;
+                        D->pf_h16[(size_t)l * 7 + i] = hp;
+                        hp += k;
+                    } else {
+                        D->pf_h16[(size_t)l * 7 + i] = static_cast<const __half*>(bl[i]->input_factor);
+                    }
+                }
+            }
+        }
+    }
+    int rc, cur = 0;
+    const int Mi = (int)M;
+    auto reduce = [&](float* t0, float* t1, float* t2, int n, int nprob, float* stats) -> int {
+        ReduceArgs r = {};
+        r.t[0] = t0; r.t[1] = t1; r.t[2] = t2; r.N[0] = r.N[1] = r.N[2] = n; r.stats = stats; r.M = Mi; r.S = 1;
+        return launch_pdl(tc5_reduce_stats_kernel, dim3(Mi, nprob, kReduceSlices), dim3(256), 0, s, r);
+    };
+    auto proj = [&](const __half* x, int K, int nprob, const onebit_bitlinear_params* const* bl, const __half* const* h16, float* const* t, int N) -> int {
+        Tc5Launch tl = {};
+        tl.x16 = x; tl.M = Mi; tl.K = K; tl.nprob = nprob; tl.ksplit = 1; tl.param_dtype = pd;
+        for (int i = 0; i < nprob; ++i) {
+            tl.p[i].w = static_cast<const int8_t*>(bl[i]->weight); tl.p[i].h16 = h16[i]; tl.p[i].g = bl[i]->weight_scale;
+            tl.p[i].t = t[i]; tl.p[i].N = N;
+        }
+        return launch_tc5(tl, s);
+    };
+    for (int l = 0; l < L; ++l) {
+        const onebit_layer_params& P = D->layers[l];
+        const __half* const* h16 = &D->pf_h16[(size_t)l * 7];
+        GlueArgs g = {};
+        g.mode = l == 0 ? GLUE_EMBED_NORM : GLUE_RESID_NORM;
+        g.M = Mi; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = xa;
+        g.t_a = t_d; g.stats_a = st_d; g.ncta_a = kReduceSlices;
+        g.resid_in = resid[cur]; g.resid_out = resid[cur ^ 1];
+        g.embed = D->embed; g.ids = reinterpret_cast<const long long*>(ids_dev); g.ln_w = P.input_layernorm;
+        g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
+        rc = glue_launch(D, g, s); if (rc) return rc;
+        cur ^= 1;
+        const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
+        float* tq[3] = {t_qkv, t_qkv + M * H, t_qkv + 2 * M * H};
+        rc = proj(xa, H, 3, qkv, h16, tq, H); if (rc) return rc;
+        rc = reduce(tq[0], tq[1], tq[2], H, 3, st_qkv); if (rc) return rc;
+        PrefillAttnArgs at = {};
+        at.t_q = tq[0]; at.t_k = tq[1]; at.t_v = tq[2]; at.stats = st_qkv; at.nslices = kReduceSlices; at.M = Mi; at.ld = H; at.n_ln = H;
+        at.B = batch; at.T = T; at.pos0 = pos0; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len;
+        at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
+        const size_t layer_cache = (size_t)C.max_batch * D->heads_l * C.max_seq_len * kHeadDim;
+        at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
+        at.q16 = q16; at.out16 = xa; at.out_ld = H; at.ln_eps = C.ln_eps;
+        rc = launch_prefill_attention(at, s); if (rc) return rc;
+        const onebit_bitlinear_params* po[1] = {&P.o};
+        float* to[1] = {t_o};
+        rc = proj(xa, H, 1, po, h16 + 3, to, H); if (rc) return rc;
+        rc = reduce(t_o, nullptr, nullptr, H, 1, st_o); if (rc) return rc;
+        g = {};
+        g.mode = GLUE_RESID_NORM; g.M = Mi; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = xa;
+        g.t_a = t_o; g.stats_a = st_o; g.ncta_a = kReduceSlices;
+        g.resid_in = resid[cur]; g.resid_out = resid[cur ^ 1]; g.ln_w = P.post_attention_layernorm;
+        g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
+        rc = glue_launch(D, g, s); if (rc) return rc;
+        cur ^= 1;
+        const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
+        float* tg[2] = {t_gu, t_gu + M * I};
+        rc = proj(xa, H, 2, gu, h16 + 4, tg, I); if (rc) return rc;
+        rc = reduce(tg[0], tg[1], nullptr, I, 2, st_gu); if (rc) return rc;
+        g = {};
+        g.mode = GLUE_SILU_MUL; g.M = Mi; g.K = I; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = xi;
+        g.t_a = tg[0]; g.stats_a = st_gu; g.ncta_a = kReduceSlices;
+        g.t_b = tg[1]; g.stats_b = st_gu + (size_t)kReduceSlices * M * 2; g.ncta_b = kReduceSlices;
+        g.ln_eps = C.ln_eps;
+        rc = glue_launch(D, g, s); if (rc) return rc;
+        const onebit_bitlinear_params* pdn[1] = {&P.down};
+        float* td[1] = {t_d};
+        rc = proj(xi, I, 1, pdn, h16 + 6, td, H); if (rc) return rc;
+        rc = reduce(t_d, nullptr, nullptr, H, 1, st_d); if (rc) return rc;
+    }
+    // ---- final norm -> fp16 x of every token
+    GlueArgs g = {};
+    g.mode = GLUE_RESID_NORM; g.M = Mi; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = xa;
+    g.t_a = t_d; g.stats_a = st_d; g.ncta_a = kReduceSlices;
+    g.resid_in = resid[cur]; g.resid_out = resid[cur ^ 1]; g.ln_w = D->final_norm; g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
+    rc = glue_launch(D, g, s); if (rc) return rc;
+    if (logits_all_dev) {  // every token's logits, 64 tokens per dense tcgen05 launch
+        for (size_t m0 = 0; m0 < M; m0 += 64) {
+            const int64_t mm = (int64_t)std::min<size_t>(64, M - m0);
+            rc = launch_dense_tc5(xa + m0 * H, D->lm_head, logits_all_dev + m0 * V, mm, H, V, s);
+            if (rc) return rc;
+        }
+    }
+    // ---- last token of every sequence: logits, greedy next id, positions for the decode steps that follow
+    gather_last_rows_kernel<<<batch, 128, 0, s>>>(xa, D->x_f16, T, H);
+    ONEBIT_CUDA_TRY(cudaGetLastError());
+    float* logits = logits_last_dev ? logits_last_dev : D->logits;
+    if (batch > 8) {
+        rc = launch_dense_tc5(D->x_f16, D->lm_head, logits, batch, H, V, s);
+    } else {
+        static bool configured[64] = {false};
+        int dev = 0;
+        ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !configured[dev]) {
+            ONEBIT_CUDA_TRY(cudaFuncSetAttribute(lm_head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            configured[dev] = true;
+        }
+        rc = launch_pdl(lm_head_kernel<8>, dim3((V + 7) / 8), dim3(256), (size_t)batch * H * 2, s, D->lm_head, (const __half*)D->x_f16,
+                        logits, V, H, batch);
+    }
+    if (rc) return rc;
+    set_positions_kernel<<<1, kMaxBatch, 0, s>>>(D->pos, pos0 + T - 1, batch);
+    ONEBIT_CUDA_TRY(cudaGetLastError());
+    rc = launch_pdl(argmax_advance_kernel, dim3(batch), dim3(1024), 0, s, (const float*)logits, V, D->ids, D->pos);
+    if (rc) return rc;
+    D->pos_hi = pos0 + T;
+    return ONEBIT_OK;
+}
+
 int onebit_decoder_gemv_only(onebit_decoder* D, int batch, void* stream) {
     ONEBIT_REQUIRE(D && batch >= 1 && batch <= D->cfg.max_batch, "decoder_gemv_only: bad arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);

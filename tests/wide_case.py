@@ -6,6 +6,7 @@ read once per process): decoder logits at real LLaMA widths against the pinned C
 Prints one JSON line: rel-L2 of the logits vs oracle/ref_port.py (fp32, the reference's op sequence
 modeling_bitllama.py:856-930,1512-1611), arg-max agreement, launches per step, decoder status."""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -24,9 +25,12 @@ def main(model, layers, tokens, batch, pdt):
     ids = torch.randint(3, config["vocab_size"], (batch, tokens), generator=torch.Generator().manual_seed(5))
     with torch.no_grad():
         want, _ = ref_port.RefPortModel(config, sd).forward(ids)
-    dec = BitLlamaDecoderB200(config, sd, max_seq_len=64, max_batch=batch,
+    dec = BitLlamaDecoderB200(config, sd, max_seq_len=max(64, tokens), max_batch=batch,
                               param_dtype=torch.float32 if pdt == "f32" else torch.float16)
-    got = dec.forward_tokens(ids).cpu().numpy()
+    if os.environ.get("ONEBIT_WIDE_PREFILL") == "1":
+        got = dec.prefill(ids, all_logits=True).cpu().numpy()
+    else:
+        got = dec.forward_tokens(ids).cpu().numpy()
     out = {"rel_l2": float(oracle.rel_l2(got, want.numpy())),
            "argmax_agree": float((got.argmax(-1) == want.numpy().argmax(-1)).mean()),
            "launches": dec.launches_per_step(), "persistent": bool(dec.persistent), "status": dec.status()}
