@@ -44,7 +44,7 @@ enum GlueMode {
 
 struct GlueArgs {
     int mode, M, K, nprob, write_x_f16;
-    int stats_from_data;  // RESID_NORM: t_a was all-reduced across ranks -> (sum, sumsq) from the data itself
+    int stats_from_data;  // RESID_NORM / SILU_MUL: (sum, sumsq) of t_a (t_b) from the data itself (all-reduced inputs; prompt pass)
     int n_ln;             // LayerNorm denominator of the producer(s) when it is not K (tensor-parallel shards); 0 = K
     const float* t_a; const float* stats_a; int ncta_a;   // previous GEMV output (already * g), [ncta][M][2] partials
     const float* t_b; const float* stats_b; int ncta_b;
@@ -162,9 +162,19 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
     }
     // ---- LayerNorm statistics of the producer(s) (bitnet.py:118), from the GEMV's per-CTA partials
     // (loaded after the big loads in program order: their fp64 conversion stalls the warp until they return)
-    if ((A.mode == GLUE_RESID_NORM && !A.stats_from_data) || A.mode == GLUE_SILU_MUL)
+    if ((A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL) && !A.stats_from_data)
         load_stat_partials(A.stats_a, A.ncta_a, A.M, m, st[0], st[1]);
-    if (A.mode == GLUE_SILU_MUL) load_stat_partials(A.stats_b, A.ncta_b, A.M, m, st[2], st[3]);
+    if (A.mode == GLUE_SILU_MUL && !A.stats_from_data) load_stat_partials(A.stats_b, A.ncta_b, A.M, m, st[2], st[3]);
+    if (A.mode == GLUE_SILU_MUL && A.stats_from_data) {  // the rows are in registers anyway: no separate statistics pass
+#pragma unroll
+        for (int i = 0; i < NV4; ++i)
+            if (i * kGlueThreads + tid < K4) {
+                st[0] += (double)((va[i].x + va[i].y) + (va[i].z + va[i].w));
+                st[1] += (double)((va[i].x * va[i].x + va[i].y * va[i].y) + (va[i].z * va[i].z + va[i].w * va[i].w));
+                st[2] += (double)((vb[i].x + vb[i].y) + (vb[i].z + vb[i].w));
+                st[3] += (double)((vb[i].x * vb[i].x + vb[i].y * vb[i].y) + (vb[i].z * vb[i].z + vb[i].w * vb[i].w));
+            }
+    }
     if (A.mode == GLUE_RESID_NORM && A.stats_from_data) {
 #pragma unroll
         for (int i = 0; i < NV4; ++i)
@@ -265,6 +275,11 @@ struct AttnArgs {
     float* out;                     // [M][H] fp32
     float ln_eps;
     int t_cap;                      // cache rows that fit in shared memory (bulk-copied up front); longer contexts stream
+    // split-KV (flash decoding): grid.z CTAs share one (sequence, head), each a contiguous slice of the context; the last
+    // one to finish (ticket) merges the partial (max, sum, numerator) records in slice order
+    int nsplit;
+    float* part;                    // [M][n_heads][nsplit][kHeadDim + 2]
+    int* tickets;                   // [M][n_heads], zero between launches
 };
 
 __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ AttnArgs A) {
@@ -277,6 +292,10 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     imma::pdl_wait();
     const int m = blockIdx.x, hd = blockIdx.y, d = threadIdx.x, lane = d & 31, warp = d >> 5;
     const int pos = min(max(A.pos[m], 0), A.max_seq - 1), T = pos + 1;  // host refuses earlier; never index past the cache
+    // this CTA's slice of the context (the whole context when nsplit == 1)
+    const int nsplit = A.nsplit, zi = blockIdx.z, chunk = (T + nsplit - 1) / nsplit;
+    const int j_lo = min(zi * chunk, T), j_hi = min(T, j_lo + chunk);
+    const bool owns_new = pos >= j_lo && pos < j_hi;  // the slice that holds the new token appends it to the cache
     __half* kc = A.kcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
     __half* vc = A.vcache + (((size_t)m * A.n_heads + hd) * A.max_seq) * kHeadDim;
     // The cached rows 0..pos-1 of this (sequence, head) are contiguous: pull them into shared memory with two bulk
@@ -313,8 +332,10 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     const float qr = d < half ? q0 * c - q1 * s : q0 * c + q1 * s;
     const float kr = d < half ? k0 * c - k1 * s : k0 * c + k1 * s;
     const float vv = (A.t_v[col + d] - mv) * rv;
-    kc[(size_t)pos * kHeadDim + d] = __float2half_rn(kr);
-    vc[(size_t)pos * kHeadDim + d] = __float2half_rn(vv);
+    if (owns_new) {
+        kc[(size_t)pos * kHeadDim + d] = __float2half_rn(kr);
+        vc[(size_t)pos * kHeadDim + d] = __float2half_rn(vv);
+    }
     if (in_smem) {
         Ks[(size_t)pos * kHeadDim + d] = __float2half_rn(kr);
         Vs[(size_t)pos * kHeadDim + d] = __float2half_rn(vv);
@@ -327,13 +348,13 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     // scores: one warp per cached position, lanes over d (4 each); 4 positions in flight per warp
     const float4 qv = *reinterpret_cast<const float4*>(&qs[4 * lane]);
     constexpr int NW = kHeadDim / 32;
-    for (int j0 = warp; j0 < T; j0 += 4 * NW) {
+    for (int j0 = j_lo + warp; j0 < j_hi; j0 += 4 * NW) {
         uint2 raw[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u * NW;
             raw[u] = make_uint2(0u, 0u);
-            if (j < T) raw[u] = *reinterpret_cast<const uint2*>(kr_base + (size_t)j * kHeadDim + 4 * lane);
+            if (j < j_hi) raw[u] = *reinterpret_cast<const uint2*>(kr_base + (size_t)j * kHeadDim + 4 * lane);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -342,12 +363,12 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
             const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].y));
             float dot = qv.x * a.x + qv.y * a.y + qv.z * b.x + qv.w * b.y;
             dot = warp_sum(dot);
-            if (lane == 0 && j < T) sc[j] = dot;
+            if (lane == 0 && j < j_hi) sc[j - j_lo] = dot;
         }
     }
     __syncthreads();
     float mx = -INFINITY;
-    for (int j = d; j < T; j += kHeadDim) mx = fmaxf(mx, sc[j]);
+    for (int j = j_lo + d; j < j_hi; j += kHeadDim) mx = fmaxf(mx, sc[j - j_lo]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) red[warp] = mx;
@@ -355,18 +376,19 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
     __syncthreads();
     float sum = 0.f;
-    for (int j = d; j < T; j += kHeadDim) {
-        const float e = expf(sc[j] - mx);
-        sc[j] = e;
+    for (int j = j_lo + d; j < j_hi; j += kHeadDim) {
+        const float e = expf(sc[j - j_lo] - mx);
+        sc[j - j_lo] = e;
         sum += e;
     }
     sum = warp_sum(sum);
     if (lane == 0) red[warp] = sum;
     __syncthreads();
-    const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+    const float total = red[0] + red[1] + red[2] + red[3];
+    const float inv = 1.f / total;
     // P.V: warp w takes positions w, w+4, ...; lane holds dims 4*lane .. 4*lane+3; partials combined through smem
     float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j0 = warp; j0 < T; j0 += 4 * NW) {
+    for (int j0 = j_lo + warp; j0 < j_hi; j0 += 4 * NW) {
         uint2 raw[4];
         float pj[4];
 #pragma unroll
@@ -374,9 +396,9 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
             const int j = j0 + u * NW;
             raw[u] = make_uint2(0u, 0u);
             pj[u] = 0.f;
-            if (j < T) {
+            if (j < j_hi) {
                 raw[u] = *reinterpret_cast<const uint2*>(vr_base + (size_t)j * kHeadDim + 4 * lane);
-                pj[u] = sc[j];
+                pj[u] = sc[j - j_lo];
             }
         }
 #pragma unroll
@@ -392,7 +414,33 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < NW; ++w) acc += sc[w * kHeadDim + d];
-    A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = acc * inv;
+    if (nsplit == 1) {
+        A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = acc * inv;
+        return;
+    }
+    // ---- split-KV: publish this slice's (max, sum, numerator); the last slice to arrive merges all of them in slice order
+    float* rec = A.part + (((size_t)m * A.n_heads + hd) * nsplit + zi) * (kHeadDim + 2);
+    rec[2 + d] = acc;
+    if (d == 0) { rec[0] = j_hi > j_lo ? mx : -INFINITY; rec[1] = j_hi > j_lo ? total : 0.f; }
+    __threadfence();
+    __syncthreads();
+    __shared__ int s_last;
+    if (d == 0) s_last = atomicAdd(&A.tickets[m * A.n_heads + hd], 1) == nsplit - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* base = A.part + ((size_t)m * A.n_heads + hd) * nsplit * (kHeadDim + 2);
+    float gm = -INFINITY;
+    for (int z = 0; z < nsplit; ++z) gm = fmaxf(gm, __ldcg(base + z * (kHeadDim + 2)));
+    float num = 0.f, den = 0.f;
+    for (int z = 0; z < nsplit; ++z) {
+        const float mz = __ldcg(base + z * (kHeadDim + 2));
+        const float f = mz == -INFINITY ? 0.f : expf(mz - gm);
+        den += __ldcg(base + z * (kHeadDim + 2) + 1) * f;
+        num += __ldcg(base + z * (kHeadDim + 2) + 2 + d) * f;
+    }
+    A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = num / den;
+    if (d == 0) A.tickets[m * A.n_heads + hd] = 0;
 }
 
 // ---- lm_head: logits[m][v] = sum_k W[v][k] * x[m][k], fp16 weights, fp32 accumulate (:1610-1611) ----
@@ -590,6 +638,11 @@ struct onebit_decoder {
     __half* h16_store = nullptr;
     __half* xI_f16 = nullptr;        // [B][I]
     float *red_o = nullptr, *red_d = nullptr;  // [max_batch][2]
+    // split-KV decode attention: slices per (sequence, head) (fixed by max_seq_len so that a captured graph stays valid),
+    // partial records, merge tickets
+    int attn_nsplit = 1;
+    float* attn_part = nullptr;
+    int* attn_tickets = nullptr;
     // persistent single-kernel step (persist_step.cu): batch <= 2, no tensor parallelism
     PersistState* persist = nullptr;
     // prompt pass (onebit_decoder_prefill): workspace for `pf_cap` tokens, allocated on first use
@@ -642,6 +695,20 @@ size_t attn_smem_bytes(int max_seq) {
         configured[dev] = true;
     }
     return (size_t)std::max(max_seq, 4 * kHeadDim) * sizeof(float) + (size_t)2 * std::min(max_seq, 384) * kHeadDim * 2;
+}
+
+// split-KV set-up shared by every decode path: fills the slice fields of `at` and returns the dynamic shared memory to launch with
+size_t attn_finish_args(const onebit_decoder* D, AttnArgs& at, int M, bool many_ctas) {
+    at.nsplit = D->attn_nsplit;
+    at.part = D->attn_part;
+    at.tickets = D->attn_tickets;
+    if (at.nsplit > 1 || many_ctas) {  // slices (or many small CTAs) stream the cached rows from L2: no shared-memory staging
+        at.t_cap = 0;
+        return (size_t)std::max(D->cfg.max_seq_len, 4 * kHeadDim) * sizeof(float);
+    }
+    at.t_cap = std::min(D->cfg.max_seq_len, 384);
+    (void)M;
+    return attn_smem_bytes(D->cfg.max_seq_len);
 }
 
 // ---- fused glue + GEMV stage (fused_gemv.cuh) -----------------------------------------------------------
@@ -769,8 +836,9 @@ int run_fused_layers(onebit_decoder* D, int M, cudaStream_t s, bool with_attenti
             at.pos = D->pos; at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
             const size_t layer_cache = (size_t)B * D->heads_l * C.max_seq_len * kHeadDim;
             at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
-            at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = std::min(C.max_seq_len, 384);
-            rc = launch_pdl(attn_kernel, dim3(M, D->heads_l), dim3(kHeadDim), attn_smem_bytes(C.max_seq_len), s, at);
+            at.out = D->attn_out; at.ln_eps = C.ln_eps;
+            const size_t asmem = attn_finish_args(D, at, M, false);
+            rc = launch_pdl(attn_kernel, dim3(M, D->heads_l, at.nsplit), dim3(kHeadDim), asmem, s, at);
             if (rc) return rc; ++*launches;
         }
         // ---- stage 3: attention output -> o_proj (row-parallel: local K slice, zero-padded to a multiple of 256)
@@ -880,9 +948,10 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         const size_t layer_cache = (size_t)B * D->heads_l * C.max_seq_len * kHeadDim;
         at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
         // many (sequence, head) CTAs: stream the cached rows from L2 instead of staging them (several CTAs per SM)
-        at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = 0;
+        at.out = D->attn_out; at.ln_eps = C.ln_eps;
+        const size_t asmem = attn_finish_args(D, at, M, true);
         if (!only_proj) {
-            rc = launch_pdl(attn_kernel, dim3(M, D->heads_l), dim3(kHeadDim), (size_t)std::max(C.max_seq_len, 4 * kHeadDim) * sizeof(float), s, at);
+            rc = launch_pdl(attn_kernel, dim3(M, D->heads_l, at.nsplit), dim3(kHeadDim), asmem, s, at);
             if (rc) return rc; ++*launches;
         }
         // ---- glue 2: attention output [M][Hk] (pad columns stay zero) -> fp16
@@ -1013,6 +1082,8 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     const size_t o_x16 = take((size_t)B * H * 2), o_ids = take(B * 8), o_ids2 = take(B * 8), o_pos = take(B * 4);
     const size_t o_rq = take((size_t)3 * kReduceSlices * B * 2 * 4), o_rg = take((size_t)2 * kReduceSlices * B * 2 * 4);
     const size_t o_ro = take((size_t)kReduceSlices * B * 2 * 4), o_rd = take((size_t)kReduceSlices * B * 2 * 4);
+    D->attn_nsplit = std::max(1, std::min(16, cfg->max_seq_len / 512));
+    const size_t o_ap = take((size_t)B * D->heads_l * D->attn_nsplit * (kHeadDim + 2) * 4), o_at = take((size_t)B * D->heads_l * 4);
     const size_t o_xI = take(big ? (size_t)B * std::max(I, D->Ik) * 2 : 16);
     const bool need_h16 = big && cfg->param_dtype != ONEBIT_F16;
     const size_t o_h16 = take(need_h16 ? (size_t)L * (5 * (size_t)H + D->Hk + D->Ik) * 2 : 16);
@@ -1034,6 +1105,7 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     D->ids = (long long*)(a + o_ids); D->ids_stage = (long long*)(a + o_ids2); D->pos = (int*)(a + o_pos);
     D->red_qkv = (float*)(a + o_rq); D->red_gu = (float*)(a + o_rg);
     D->red_o = (float*)(a + o_ro); D->red_d = (float*)(a + o_rd);
+    D->attn_part = (float*)(a + o_ap); D->attn_tickets = (int*)(a + o_at);
     D->xI_f16 = (__half*)(a + o_xI);
     D->h16_store = (__half*)(a + o_h16);
     if (big) {  // the tcgen05 A operand folds input_factor in as fp16: one-time copies when the parameters are bf16 / fp32
@@ -1182,8 +1254,9 @@ static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced
         at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
         const size_t layer_cache = (size_t)C.max_batch * D->heads_l * C.max_seq_len * kHeadDim;
         at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
-        at.out = D->attn_out; at.ln_eps = C.ln_eps; at.t_cap = std::min(C.max_seq_len, 384);
-        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads), dim3(kHeadDim), attn_smem_bytes(C.max_seq_len), s, at);
+        at.out = D->attn_out; at.ln_eps = C.ln_eps;
+        const size_t asmem2 = attn_finish_args(D, at, M, false);
+        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads, at.nsplit), dim3(kHeadDim), asmem2, s, at);
         if (rc) return rc; ++launches;
         // ---- glue 2: attention output -> o digits
         g = {};
@@ -1342,11 +1415,8 @@ int onebit_decoder_prefill(onebit_decoder* D, int batch, int T, int pos0, const 
     }
     int rc, cur = 0;
     const int Mi = (int)M;
-    auto reduce = [&](float* t0, float* t1, float* t2, int n, int nprob, float* stats) -> int {
-        ReduceArgs r = {};
-        r.t[0] = t0; r.t[1] = t1; r.t[2] = t2; r.N[0] = r.N[1] = r.N[2] = n; r.stats = stats; r.M = Mi; r.S = 1;
-        return launch_pdl(tc5_reduce_stats_kernel, dim3(Mi, nprob, kReduceSlices), dim3(256), 0, s, r);
-    };
+    // (no statistics pass: every consumer — glue kernels, q/k/v preparation — holds its token's whole rows and takes the
+    // LayerNorm sums from them)
     auto proj = [&](const __half* x, int K, int nprob, const onebit_bitlinear_params* const* bl, const __half* const* h16, float* const* t, int N) -> int {
         Tc5Launch tl = {};
         tl.x16 = x; tl.M = Mi; tl.K = K; tl.nprob = nprob; tl.ksplit = 1; tl.param_dtype = pd;
@@ -1362,7 +1432,7 @@ int onebit_decoder_prefill(onebit_decoder* D, int batch, int T, int pos0, const 
         GlueArgs g = {};
         g.mode = l == 0 ? GLUE_EMBED_NORM : GLUE_RESID_NORM;
         g.M = Mi; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = xa;
-        g.t_a = t_d; g.stats_a = st_d; g.ncta_a = kReduceSlices;
+        g.t_a = t_d; g.stats_a = st_d; g.ncta_a = kReduceSlices; g.stats_from_data = 1;
         g.resid_in = resid[cur]; g.resid_out = resid[cur ^ 1];
         g.embed = D->embed; g.ids = reinterpret_cast<const long long*>(ids_dev); g.ln_w = P.input_layernorm;
         g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
@@ -1371,9 +1441,8 @@ int onebit_decoder_prefill(onebit_decoder* D, int batch, int T, int pos0, const 
         const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
         float* tq[3] = {t_qkv, t_qkv + M * H, t_qkv + 2 * M * H};
         rc = proj(xa, H, 3, qkv, h16, tq, H); if (rc) return rc;
-        rc = reduce(tq[0], tq[1], tq[2], H, 3, st_qkv); if (rc) return rc;
         PrefillAttnArgs at = {};
-        at.t_q = tq[0]; at.t_k = tq[1]; at.t_v = tq[2]; at.stats = st_qkv; at.nslices = kReduceSlices; at.M = Mi; at.ld = H; at.n_ln = H;
+        at.t_q = tq[0]; at.t_k = tq[1]; at.t_v = tq[2]; at.M = Mi; at.ld = H; at.n_ln = H;
         at.B = batch; at.T = T; at.pos0 = pos0; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len;
         at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
         const size_t layer_cache = (size_t)C.max_batch * D->heads_l * C.max_seq_len * kHeadDim;
@@ -1383,10 +1452,9 @@ int onebit_decoder_prefill(onebit_decoder* D, int batch, int T, int pos0, const 
         const onebit_bitlinear_params* po[1] = {&P.o};
         float* to[1] = {t_o};
         rc = proj(xa, H, 1, po, h16 + 3, to, H); if (rc) return rc;
-        rc = reduce(t_o, nullptr, nullptr, H, 1, st_o); if (rc) return rc;
         g = {};
         g.mode = GLUE_RESID_NORM; g.M = Mi; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = xa;
-        g.t_a = t_o; g.stats_a = st_o; g.ncta_a = kReduceSlices;
+        g.t_a = t_o; g.stats_a = st_o; g.ncta_a = kReduceSlices; g.stats_from_data = 1;
         g.resid_in = resid[cur]; g.resid_out = resid[cur ^ 1]; g.ln_w = P.post_attention_layernorm;
         g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
         rc = glue_launch(D, g, s); if (rc) return rc;
@@ -1394,22 +1462,20 @@ int onebit_decoder_prefill(onebit_decoder* D, int batch, int T, int pos0, const 
         const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
         float* tg[2] = {t_gu, t_gu + M * I};
         rc = proj(xa, H, 2, gu, h16 + 4, tg, I); if (rc) return rc;
-        rc = reduce(tg[0], tg[1], nullptr, I, 2, st_gu); if (rc) return rc;
         g = {};
         g.mode = GLUE_SILU_MUL; g.M = Mi; g.K = I; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = xi;
-        g.t_a = tg[0]; g.stats_a = st_gu; g.ncta_a = kReduceSlices;
+        g.t_a = tg[0]; g.stats_a = st_gu; g.ncta_a = kReduceSlices; g.stats_from_data = 1;
         g.t_b = tg[1]; g.stats_b = st_gu + (size_t)kReduceSlices * M * 2; g.ncta_b = kReduceSlices;
         g.ln_eps = C.ln_eps;
         rc = glue_launch(D, g, s); if (rc) return rc;
         const onebit_bitlinear_params* pdn[1] = {&P.down};
         float* td[1] = {t_d};
         rc = proj(xi, I, 1, pdn, h16 + 6, td, H); if (rc) return rc;
-        rc = reduce(t_d, nullptr, nullptr, H, 1, st_d); if (rc) return rc;
     }
     // ---- final norm -> fp16 x of every token
     GlueArgs g = {};
     g.mode = GLUE_RESID_NORM; g.M = Mi; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = xa;
-    g.t_a = t_d; g.stats_a = st_d; g.ncta_a = kReduceSlices;
+    g.t_a = t_d; g.stats_a = st_d; g.ncta_a = kReduceSlices; g.stats_from_data = 1;
     g.resid_in = resid[cur]; g.resid_out = resid[cur ^ 1]; g.ln_w = D->final_norm; g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
     rc = glue_launch(D, g, s); if (rc) return rc;
     if (logits_all_dev) {  // every token's logits, 64 tokens per dense tcgen05 launch

@@ -31,37 +31,55 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// grid (T, heads, B), 128 threads (one per head dimension)
-__global__ void __launch_bounds__(kD) qkv_prep_kernel(const PrefillAttnArgs A) {
-    const int t = blockIdx.x, hd = blockIdx.y, b = blockIdx.z, d = threadIdx.x;
-    const int m = b * A.T + t, pos = A.pos0 + t;
-    const float n_inv = 1.f / (float)A.n_ln;
-    float mean[3], rstd[3];
+// grid (T, B), 256 threads: one CTA per token. LayerNorm sums of the token's q / k / v rows straight from the rows
+// (coalesced float4 pass), then LayerNorm + RoPE + cache append + Q staging for every head.
+__global__ void __launch_bounds__(256) qkv_prep_kernel(const PrefillAttnArgs A) {
+    __shared__ double red[8][6];
+    __shared__ float s_mean[3], s_rstd[3];
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = b * A.T + t, pos = A.pos0 + t, W = A.n_heads * kD;  // W = row width (local heads)
+    const float* rows[3] = {A.t_q + (size_t)m * A.ld, A.t_k + (size_t)m * A.ld, A.t_v + (size_t)m * A.ld};
+    double st[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {  // per-token statistics: nslices partial (sum, sumsq) records per projection
-        double s = 0.0, q = 0.0;
-        for (int z = 0; z < A.nslices; ++z) {
-            const float2 v = *reinterpret_cast<const float2*>(A.stats + (((size_t)p * A.nslices + z) * A.M + m) * 2);
-            s += (double)v.x;
-            q += (double)v.y;
+    for (int p = 0; p < 3; ++p)
+        for (int i = tid; i < W / 4; i += 256) {
+            const float4 v = reinterpret_cast<const float4*>(rows[p])[i];
+            st[2 * p] += (double)((v.x + v.y) + (v.z + v.w));
+            st[2 * p + 1] += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
         }
-        const double mu = s * (double)n_inv, var = fmax(q * (double)n_inv - mu * mu, 0.0);
-        mean[p] = (float)mu;
-        rstd[p] = (float)(1.0 / sqrt(var + (double)A.ln_eps));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) st[k] += __shfl_xor_sync(0xffffffffu, st[k], o);
+        if (lane == 0) red[warp][k] = st[k];
     }
-    const size_t col = (size_t)m * A.ld + hd * kD;
-    const int half = kD / 2, dp = d < half ? d + half : d - half, fi = d < half ? d : d - half;
-    const float c = A.rope_cos[(size_t)pos * half + fi], s = A.rope_sin[(size_t)pos * half + fi];
-    const float q0 = (A.t_q[col + d] - mean[0]) * rstd[0], q1 = (A.t_q[col + dp] - mean[0]) * rstd[0];
-    const float k0 = (A.t_k[col + d] - mean[1]) * rstd[1], k1 = (A.t_k[col + dp] - mean[1]) * rstd[1];
-    const float qr = d < half ? q0 * c - q1 * s : q0 * c + q1 * s;  // rotate_half: (-x2, x1)
-    const float kr = d < half ? k0 * c - k1 * s : k0 * c + k1 * s;
-    const float vv = (A.t_v[col + d] - mean[2]) * rstd[2];
-    const size_t crow = (((size_t)b * A.n_heads + hd) * A.max_seq + pos) * kD + d;
-    A.kcache[crow] = __float2half_rn(kr);
-    A.vcache[crow] = __float2half_rn(vv);
-    // 1 / sqrt(128) (:546) and log2(e) (the softmax below uses exp2) folded into Q
-    A.q16[(((size_t)b * A.n_heads + hd) * A.T + t) * kD + d] = __float2half_rn(qr * (0.08838834764831845f * 1.4426950408889634f));
+    __syncthreads();
+    if (tid < 3) {
+        double s = 0.0, q = 0.0;
+        for (int w = 0; w < 8; ++w) { s += red[w][2 * tid]; q += red[w][2 * tid + 1]; }
+        const double mu = s / (double)A.n_ln, var = fmax(q / (double)A.n_ln - mu * mu, 0.0);
+        s_mean[tid] = (float)mu;
+        s_rstd[tid] = (float)(1.0 / sqrt(var + (double)A.ln_eps));
+    }
+    __syncthreads();
+    const float mq = s_mean[0], rq = s_rstd[0], mk = s_mean[1], rk = s_rstd[1], mv = s_mean[2], rv = s_rstd[2];
+    const int half = kD / 2;
+    for (int e = tid; e < W; e += 256) {
+        const int hd = e >> 7, d = e & (kD - 1);
+        const int dp = d < half ? d + half : d - half, fi = d < half ? d : d - half;
+        const float c = A.rope_cos[(size_t)pos * half + fi], s = A.rope_sin[(size_t)pos * half + fi];
+        const int col = hd * kD;
+        const float q0 = (rows[0][col + d] - mq) * rq, q1 = (rows[0][col + dp] - mq) * rq;
+        const float k0 = (rows[1][col + d] - mk) * rk, k1 = (rows[1][col + dp] - mk) * rk;
+        const float qr = d < half ? q0 * c - q1 * s : q0 * c + q1 * s;  // rotate_half: (-x2, x1)
+        const float kr = d < half ? k0 * c - k1 * s : k0 * c + k1 * s;
+        const float vv = (rows[2][col + d] - mv) * rv;
+        const size_t crow = (((size_t)b * A.n_heads + hd) * A.max_seq + pos) * kD + d;
+        A.kcache[crow] = __float2half_rn(kr);
+        A.vcache[crow] = __float2half_rn(vv);
+        // 1 / sqrt(128) (:546) and log2(e) (the softmax below uses exp2) folded into Q
+        A.q16[(((size_t)b * A.n_heads + hd) * A.T + t) * kD + d] = __float2half_rn(qr * (0.08838834764831845f * 1.4426950408889634f));
+    }
 }
 
 // grid (ceil(T / 64), heads, B), 128 threads
@@ -189,7 +207,7 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const PrefillAttnArgs
 
 int launch_prefill_attention(const PrefillAttnArgs& A, cudaStream_t s) {
     ONEBIT_REQUIRE(A.T >= 1 && A.B >= 1 && A.pos0 >= 0 && A.pos0 + A.T <= A.max_seq, "prefill attention: the prompt does not fit the KV cache");
-    qkv_prep_kernel<<<dim3(A.T, A.n_heads, A.B), kD, 0, s>>>(A);
+    qkv_prep_kernel<<<dim3(A.T, A.B), 256, 0, s>>>(A);
     ONEBIT_CUDA_TRY(cudaGetLastError());
     prefill_attn_kernel<<<dim3((A.T + kBQ - 1) / kBQ, A.n_heads, A.B), 128, 0, s>>>(A);
     ONEBIT_CUDA_TRY(cudaGetLastError());

@@ -6,8 +6,7 @@ namespace onebit {
 
 struct PrefillAttnArgs {
     const float* t_q; const float* t_k; const float* t_v;  // [M = B*T][ld] fp32 BitLinear outputs (already * weight_scale)
-    const float* stats;   // [3][nslices][M][2] partial (sum, sum of squares) per token and projection
-    int nslices, M, ld, n_ln;
+    int M, ld, n_ln;      // tokens, row stride of t_q/t_k/t_v, LayerNorm denominator (rows of the full q/k/v layers)
     int B, T, pos0, n_heads, max_seq;
     const float* rope_cos; const float* rope_sin;  // [max_seq][64]
     __half* kcache; __half* vcache;                // [B_cache][n_heads][max_seq][128] of this layer

@@ -274,3 +274,21 @@ def test_prefill_at_llama7b_width_matches_the_reference_port():
     out = _wide("7b", 2, 96, 2, "f16", ONEBIT_WIDE_PREFILL="1")
     assert out["rel_l2"] < 3e-3, out
     assert out["argmax_agree"] > 0.95, out
+
+
+def test_split_kv_decode_attention_matches_the_reference_port(tiny):
+    """max_seq_len 1536 -> three context slices per (sequence, head), merged by the last CTA to finish (flash decoding):
+    a 300-token teacher-forced pass vs the pinned CPU port, and bit-equality of two runs (fixed merge order)."""
+    from oracle import ref_port
+    config, sd, z = tiny
+    ids = torch.randint(3, config["vocab_size"], (2, 300), generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        want, _ = ref_port.RefPortModel(config, sd).forward(ids)
+    dec = BitLlamaDecoderB200(config, sd, max_seq_len=1536, max_batch=2, param_dtype=torch.float32)
+    got = dec.forward_tokens(ids)
+    again = dec.forward_tokens(ids)
+    assert torch.equal(got, again)
+    assert dec.status() == 0
+    dec.close()
+    for lo, hi in [(0, 40), (260, 300)]:
+        assert oracle.rel_l2(got[:, lo:hi].cpu().numpy(), want.numpy()[:, lo:hi]) < 3e-3
