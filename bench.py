@@ -188,10 +188,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         """Decode throughput of one replica per GPU at batch B: device-resident loop, end-to-end loop with host ids in and
         out every step, and the BitLinear projection launches of a step on their own (roofline of the dominant kernel)."""
         prompt_len = 16
-        sd = synthetic_state_dict(cfg, seed=rank)
-        dec = BitLlamaDecoderB200(cfg, sd, device=dev, max_seq_len=prompt_len + 2 * (K + W) + 32, max_batch=B)
+        tp = bool(args.tp) and world > 1
+        sd = synthetic_state_dict(cfg, seed=0 if tp else rank)  # (a tensor-parallel replica: every rank shards the same model)
+        dec = BitLlamaDecoderB200(cfg, sd, device=dev, max_seq_len=prompt_len + 2 * (K + W) + 32, max_batch=B,
+                                  tp_group=dist.group.WORLD if tp else None)
         del sd
-        gen = torch.Generator().manual_seed(1234 + rank)
+        nrep = 1 if tp else world  # replicas whose tokens add up
+        gen = torch.Generator().manual_seed(1234 + (0 if tp else rank))
         prompt = torch.randint(3, cfg["vocab_size"], (B, prompt_len), generator=gen)
 
         def prefill():
@@ -214,8 +217,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        out = {"batch": B, "value": world * B * K / (ms * 1e-3), "ms_per_step": ms / K, "launches_per_step": dec.launches_per_step(),
-               "prompt_len": prompt_len}
+        out = {"batch": B, "value": nrep * B * K / (ms * 1e-3), "ms_per_step": ms / K, "launches_per_step": dec.launches_per_step(),
+               "prompt_len": prompt_len, "tp_allreduce": getattr(dec, "tp_allreduce", "none")}
         # ---- end to end through the public API: ids from pinned host memory in, next ids back to the host, every step
         if with_e2e:
             prefill()
@@ -238,8 +241,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             e3.record()
             barrier()
             ms_e2e = max_over_ranks(e2.elapsed_time(e3))
-            out["e2e"] = {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * B,
+            out["e2e"] = {"value": nrep * B * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * B,
                           "d2h_bytes_per_step": 8 * B, "ms_per_step": ms_e2e / K}
+        if tp:  # (the per-kernel roofline is reported by the single-GPU runs; a tensor-parallel step is collective-latency-bound)
+            dec.close()
+            del dec
+            torch.cuda.empty_cache()
+            return out
         # ---- dominant kernel alone: the 4 x L BitLinear projection launches of a step, back to back, CUDA events
         bb = bitlinear_bytes(cfg, B)
         g = torch.cuda.CUDAGraph()
@@ -306,27 +314,46 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 extra[label] = r
             except Exception as exc:  # the headline line must survive a failure of the secondary operating point
                 extra[label] = {"error": str(exc)[:300]}
+    if B == 1 and world == 1 and os.environ.get("ONEBIT_BENCH_EXTRA", "1") != "0":
+        # BASELINE configs[2]: prompt pass 2048 tokens x batch 8 through the tcgen05 prefill tile, then 128 decode steps
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "tools" / "bench_config3.py"), "--model", args.model], capture_output=True,
+                               text=True, timeout=400)
+            extra["prefill2048_decode128_b8"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else \
+                {"error": r.stderr[-300:]}
+        except Exception as exc:
+            extra["prefill2048_decode128_b8"] = {"error": str(exc)[:300]}
     if world > 1:
+        # (no destroy_process_group: it blocks while CUDA graphs that captured collective kernels exist; see tools/tp_check.py)
+        torch.cuda.synchronize(dev)
         dist.barrier()
-        dist.destroy_process_group()
     if rank != 0:
-        return
+        sys.stdout.flush()
+        os._exit(0)
     cpu = cpu_decode_baseline(cfg, B, tokens=3) if world == 1 else None
     line = {"metric": metric, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if (args.tp and world > 1) else "weak", "vs_baseline": None,
             "dtype": "int8" if B <= 4 else "f16", "data": "synthetic",
             "config": {"workload": f"{name} greedy decode, batch {B} per GPU, {main_res['prompt_len']}-token prompt then {K} "
                                    f"generated tokens, static KV cache, one CUDA-graph replay per step",
-                       "replicas": world, "l2": "per-step weight stream 1.07 GB > 126 MB L2 (no flush needed)",
+                       "replicas": 1 if (args.tp and world > 1) else world,
+                       "parallelism": (f"tp{world}: one tensor-parallel replica, 4 all-reduces per layer ({main_res.get('tp_allreduce')}: "
+                                       "one-shot Lamport all-reduce over NVLink peer memory, csrc/p2p_allreduce.cu)"
+                                       if (args.tp and world > 1) else f"{world} independent replica(s), no data-path collective"),
+                       "l2": "per-step weight stream 1.07 GB > 126 MB L2 (no flush needed)",
                        "activation_dtype": ("fp32 residual / fp16 KV cache / 23-bit integer BitLinear inputs" if B <= 4 else
                                             "fp32 residual / fp16 KV cache / fp16 BitLinear inputs (tcgen05 kind::f16, fp32 accumulate)")},
             "e2e": main_res["e2e"],
             "gpu_launches": main_res["launches_per_step"] * K, "launches_per_step": main_res["launches_per_step"],
-            "roofline": main_res["roofline"], "clocks": clocks}
+            "roofline": main_res.get("roofline"), "clocks": clocks}
     line.update(extra)
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
+    if world > 1:
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
@@ -337,6 +364,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("ONEBIT_BENCH_BATCH", "1")))
     ap.add_argument("--model", default=os.environ.get("ONEBIT_BENCH_MODEL", "7b"), choices=["7b", "13b"])
+    ap.add_argument("--tp", action="store_true", default=os.environ.get("ONEBIT_BENCH_TP", "0") == "1",
+                    help="ONE tensor-parallel replica over all ranks (BASELINE configs[4]) instead of independent replicas")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
