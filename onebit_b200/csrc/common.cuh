@@ -96,6 +96,7 @@ struct Tc5LaunchProblem {
 struct Tc5Launch {
     const __half* x16;  // [M][K]
     int M, K, nprob, ksplit, param_dtype;
+    int bf16;           // x16 and h16 hold bfloat16 (else fp16)
     Tc5LaunchProblem p[3];
 };
 int launch_tc5(const Tc5Launch& L, cudaStream_t s);

@@ -83,8 +83,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return d;
 }
 // kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
-__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N, bool bf16) {
+    const uint32_t ab = bf16 ? ((1u << 7) | (1u << 10)) : 0u;  // A / B element format: 0 = F16, 1 = BF16
+    return (1u << 4) | ab | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -123,6 +124,7 @@ struct PrefillArgs {
     Tc5Problem p[kMaxProblems];
     int nprob, M, K, ksplit;
     int wtma;  // packed signs arrive through TMA slabs (K % 128 == 0); else the expanders load them themselves
+    int bf16;  // activations and the input_factor copy are bfloat16 (same bit tricks: the sign is bit 15 of either format)
 };
 
 template <typename TP, int HALVES, int TM, bool DENSE>
@@ -216,7 +218,7 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(128, umma_n);
+            const uint32_t idesc = umma_idesc_f16(128, umma_n, A.bf16 != 0);
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % kStages, ph = (c / kStages) & 1;
                 mbar_wait(&full_a[s], ph);
@@ -359,6 +361,12 @@ __global__ void to_half_kernel(const TX* __restrict__ x, __half* __restrict__ y,
     if (i < n) y[i] = __float2half_rn(to_f32(x[i]));
 }
 
+template <typename TX>
+__global__ void to_bf16_kernel(const TX* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2bfloat16_rn(to_f32(x[i]));
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -375,14 +383,14 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int encode_2d(CUtensorMap* map, const __half* base, int64_t rows, int64_t k, int box_rows) {
+int encode_2d(CUtensorMap* map, const __half* base, int64_t rows, int64_t k, int box_rows, bool bf16 = false) {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) return fail(ONEBIT_ERR_CUDA, "tcgen05 path: cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
     const cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+    CUresult cr = encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(ONEBIT_ERR_CUDA, "tcgen05 path: cuTensorMapEncodeTiled failed, code " + std::to_string((int)cr));
@@ -428,7 +436,7 @@ bool prefill_tc5_supported(int64_t m, int64_t k, int64_t n) {
 size_t prefill_tc5_workspace_bytes(int64_t m, int64_t k, int act_dtype, int param_dtype) {
     size_t b = 0;
     if (act_dtype != ONEBIT_F16) b += (((size_t)m * k * 2) + 255) & ~(size_t)255;
-    if (param_dtype != ONEBIT_F16) b += (((size_t)k * 2) + 255) & ~(size_t)255;
+    b += (((size_t)k * 2) + 255) & ~(size_t)255;  // input_factor copy in the activation-side 16-bit format
     return b + 256;
 }
 
@@ -445,22 +453,36 @@ int launch_prefill_tc5(const void* x, const int8_t* w, const void* g, const void
                        int64_t n, int act_dtype, int param_dtype, bool scale_by_g, void* workspace, cudaStream_t s) {
     ONEBIT_REQUIRE(prefill_tc5_supported(m, k, n), "prefill_tc5: needs K % 64 == 0");
     char* ws = static_cast<char*>(workspace);
+    // bfloat16 activations stay bfloat16 (tcgen05 kind::f16 takes BF16 operands; a conversion to fp16 would overflow beyond
+    // 65504 and flush small values — ADVICE r01). fp32 activations are rounded to fp16: values beyond the fp16 range saturate
+    // (documented in onebit_b200.h; the bit-plane GEMV of M <= 8 keeps 23 bits).
+    const bool bf = act_dtype == ONEBIT_BF16;
     const __half* x16 = static_cast<const __half*>(x);
-    if (act_dtype != ONEBIT_F16) {
+    if (act_dtype == ONEBIT_F32) {
         __half* buf = reinterpret_cast<__half*>(ws);
         ws += (((size_t)m * k * 2) + 255) & ~(size_t)255;
         const int rc = launch_to_half(x, buf, m * k, act_dtype, s);
         if (rc) return rc;
         x16 = buf;
+    } else if (bf) {
+        ws += (((size_t)m * k * 2) + 255) & ~(size_t)255;  // (slot reserved by prefill_tc5_workspace_bytes, unused)
     }
     const __half* h16 = static_cast<const __half*>(h);
-    if (param_dtype != ONEBIT_F16) {
+    if (bf && param_dtype != ONEBIT_BF16) {  // input_factor as bfloat16 next to bfloat16 activations
+        __nv_bfloat16* buf = reinterpret_cast<__nv_bfloat16*>(ws);
+        const unsigned grid = (unsigned)((k + 255) / 256);
+        if (param_dtype == ONEBIT_F16) to_bf16_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(h), buf, k);
+        else to_bf16_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(h), buf, k);
+        ONEBIT_CUDA_TRY(cudaGetLastError());
+        h16 = reinterpret_cast<const __half*>(buf);
+    } else if (!bf && param_dtype != ONEBIT_F16) {
         __half* buf = reinterpret_cast<__half*>(ws);
         const int rc = launch_to_half(h, buf, k, param_dtype, s);
         if (rc) return rc;
         h16 = buf;
     }
     Tc5Launch L = {};
+    L.bf16 = bf ? 1 : 0;
     L.x16 = x16; L.M = (int)m; L.K = (int)k; L.nprob = 1; L.ksplit = 1; L.param_dtype = param_dtype;
     L.p[0].w = w; L.p[0].h16 = h16; L.p[0].g = scale_by_g ? g : nullptr; L.p[0].t = t; L.p[0].N = (int)n;
     return launch_tc5(L, s);
@@ -475,10 +497,10 @@ int launch_tc5(const Tc5Launch& L, cudaStream_t s) {
     const int tile_n = small ? 128 : 256, tile_m = small ? 64 : 256;
     ONEBIT_REQUIRE(small || L.ksplit == 1, "launch_tc5: split-K is built for the decode tile configuration only");
     CUtensorMap xmap;
-    int rc = encode_2d(&xmap, L.x16, L.M, L.K, tile_m);
+    int rc = encode_2d(&xmap, L.x16, L.M, L.K, tile_m, L.bf16 != 0);
     if (rc) return rc;
     PrefillArgs a = {};
-    a.nprob = L.nprob; a.M = L.M; a.K = L.K; a.ksplit = L.ksplit;
+    a.nprob = L.nprob; a.M = L.M; a.K = L.K; a.ksplit = L.ksplit; a.bf16 = L.bf16;
     a.wtma = (L.K % 128 == 0) ? 1 : 0;
     ONEBIT_REQUIRE(L.ksplit == 1 || L.K / kChunkK / 2 >= L.ksplit, "launch_tc5: K too small for this split");
     CUtensorMap wm[3];

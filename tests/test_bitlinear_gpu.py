@@ -413,3 +413,28 @@ def test_auto_dispatch_picks_a_tensor_core_variant_for_every_llama_batch():
     assert np.array_equal(a, b)
     case = oracle.synth_case(2201, 4096, 4096, 2)
     assert np.array_equal(run(case, "f16", "auto"), run(case, "f16", "mma"))
+
+
+def test_tcgen05_bfloat16_activations_keep_their_range():
+    """bf16 activations used to be rounded to fp16 on the tcgen05 path (|x| > 65504 -> inf, tiny values flushed).
+    They now stay bf16 through the MMA (kind::f16 with BF16 operands): inputs far outside the fp16 range must match the
+    oracle evaluated on the same bf16 values."""
+    case = oracle.synth_case(2300, 1024, 384, 40)
+    x = case["x"].copy()
+    x[::3] *= 3.0e5     # beyond the fp16 maximum
+    x[1::3] *= 1.0e-7   # below the fp16 subnormal range
+    c2 = dict(case, x=torch.from_numpy(x).bfloat16().float().numpy())
+    for key in ("g", "h"):
+        c2[key] = torch.from_numpy(case[key]).bfloat16().float().numpy()
+    d = dev()
+    t = onebit_b200.bitlinear_matvec(torch.from_numpy(c2["x"]).to(d, torch.bfloat16), torch.from_numpy(c2["packed"]).to(d),
+                                     torch.from_numpy(c2["g"]).to(d, torch.bfloat16), torch.from_numpy(c2["h"]).to(d, torch.bfloat16),
+                                     scale_by_g=True, variant="tc5")
+    _, want_u = oracle.bitlinear_forward_c(c2["x"], c2["packed"], c2["g"], c2["h"], None, return_pre_ln=True)
+    got = t.cpu().numpy()
+    assert np.isfinite(got).all()
+    for rows in (slice(0, None, 3), slice(1, None, 3), slice(2, None, 3)):  # per magnitude class (a global norm would hide the small rows)
+        assert oracle.rel_l2(got[rows], want_u[rows]) < 1e-5
+    # fp16 parameters next to bf16 activations: input_factor is re-rounded to bf16 (documented), result stays finite and close
+    y = run(dict(c2, bias=None), "bf16", "tc5", param="f16")
+    assert np.isfinite(y).all()
