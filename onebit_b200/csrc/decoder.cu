@@ -886,10 +886,11 @@ int run_fused_layers(onebit_decoder* D, int M, cudaStream_t s, bool with_attenti
     return ONEBIT_OK;
 }
 
-// split-K factor of a batched-decode projection launch: about four CTAs per SM (measured better than one exact wave of
-// longer CTAs: 4.27 vs 4.55 ms per LLaMA-7B step at batch 32), at least 4 K chunks per CTA
+// split-K factor of a batched-decode projection launch: the decode tile runs 3 CTAs per SM (registers, shared memory);
+// fill one wave of those slots, never overshoot it (a second, mostly empty wave costs a whole CTA lifetime), at least 4 K
+// chunks per CTA
 int tc5_ksplit(int row_tiles, int K, int ksplit_max) {
-    const int want = (4 * num_sms() + row_tiles - 1) / row_tiles;
+    const int want = std::max(1, 3 * num_sms() / row_tiles);
     return std::max(1, std::min(std::min(want, ksplit_max), K / 64 / 4));
 }
 

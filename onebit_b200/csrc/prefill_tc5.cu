@@ -128,7 +128,7 @@ struct PrefillArgs {
 };
 
 template <typename TP, int HALVES, int TM, bool DENSE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, HALVES == 2 ? 1 : 3)  // decode tile: 3 CTAs per SM (<= 68 registers)
 prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap amap,
                    const __grid_constant__ CUtensorMap wmap1, const __grid_constant__ CUtensorMap wmap2,
                    const __grid_constant__ PrefillArgs A) {
@@ -164,14 +164,14 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_a[s], DENSE ? 1 : kExpanders);
+            mbar_init(&full_a[s], DENSE ? 1 : kExpanders / 32);  // one arrival per expander warp
             mbar_init(&full_b[s], 1);
             mbar_init(&empty[s], 1);
         }
         mbar_init(&tmem_full, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&wfull[s], 1);
-            mbar_init(&wempty[s], kExpanders);
+            mbar_init(&wempty[s], kExpanders / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
@@ -274,7 +274,8 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                 q0[2 * i] = make_uint2(v.x, v.y);
                 q0[2 * i + 1] = make_uint2(v.z, v.w);
             }
-            mbar_arrive(&wempty[b]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&wempty[b]);
           }
 #pragma unroll
           for (int ci = 0; ci < kPF; ++ci) {
@@ -309,7 +310,8 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             TC5_STAMP(tr0 && e2 == 0 && c < 40, 256 + 2 * c);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
             TC5_STAMP(tr0 && e2 == 0 && c < 40, 257 + 2 * c);
-            mbar_arrive(&full_a[s]);
+            __syncwarp();  // one arrival per warp: 256 arrivals on one shared-memory word per chunk serialise
+            if (lane == 0) mbar_arrive(&full_a[s]);
             TC5_STAMP(tr0 && e2 == 0 && c < 40, 17 + 4 * c);
           }
         }
@@ -420,6 +422,7 @@ int launch_inst(const CUtensorMap& xmap, const CUtensorMap* wm, const PrefillArg
     ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<HALVES, TM>::kSmemBytes));
+        ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured[dev] = true;
     }
     kern<<<grid, kThreads, Tile<HALVES, TM>::kSmemBytes, s>>>(xmap, wm[0], wm[1], wm[2], a);
