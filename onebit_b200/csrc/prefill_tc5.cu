@@ -19,6 +19,8 @@
 // warps 2-5 = sign expanders, then epilogue (tcgen05.ld -> * g -> coalesced fp32 stores).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace onebit {
@@ -356,6 +358,207 @@ prefill_tc5_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TL::kTmemCols) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Decode tile with the A operand in TENSOR MEMORY ("TS" form of tcgen05.mma): the expanders write the sign-expanded
+// (+-h) tile straight from registers into TMEM with tcgen05.st — no shared-memory copy of A, and above all no
+// generic->async proxy fence per chunk (fence.proxy.async = MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, which with several CTAs per SM
+// waits behind the other CTAs' TMA traffic: measured 0.64 us per chunk per SM with 3 CTAs against 0.35 us for a lone CTA).
+// Layout: 128 weight rows <-> 128 TMEM lanes (a warp reaches the 32 lanes of its quarter, warp % 4), a 64-column K chunk
+// <-> 32 TMEM columns (two fp16 per column, K-major); the MMA of K step k reads columns [8k, 8k + 8) of the stage.
+// TMEM plan (128 columns per CTA): accumulator 64 | two A stages of 32.
+constexpr int kTsStages = 2;
+constexpr int kTsTM = 64;
+constexpr int kTsSlabBytes = 128 * 8 * 8;
+constexpr int kTsBBytes = kTsTM * kChunkK * 2;
+constexpr int kTsSmemBytes = kTsStages * kTsBBytes + 2 * kTsSlabBytes + 1024;
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
+template <typename TP>
+__global__ void __launch_bounds__(kThreads, 3)
+tc5_decode_ts_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap0,
+                     const __grid_constant__ CUtensorMap wmap1, const __grid_constant__ CUtensorMap wmap2,
+                     const __grid_constant__ PrefillArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sB = smem;                              // [stage][64 tokens][128 B] swizzled (TMA)
+    unsigned char* sW = sB + kTsStages * kTsBBytes;        // [2][128 rows][64 B] packed-sign slabs of 8 chunks (TMA)
+    __shared__ __align__(8) uint64_t full_a[kTsStages], full_b[kTsStages], empty[kTsStages], tmem_full, wfull[2], wempty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint4 h_stage[256];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxProblems; ++i)
+        if (i < A.nprob && (int)blockIdx.x >= A.p[i].tile_begin) pi = i;
+    const Tc5Problem& P = A.p[pi];
+    const int n0 = ((int)blockIdx.x - P.tile_begin) * 128;
+    const int nchunks_all = A.K / kChunkK, half_all = nchunks_all >> 1;
+    const int c_begin = 2 * (int)(((long long)half_all * blockIdx.z) / A.ksplit);
+    const int c_end = (int)blockIdx.z + 1 == A.ksplit ? nchunks_all : 2 * (int)(((long long)half_all * (blockIdx.z + 1)) / A.ksplit);
+    const int nchunks = c_end - c_begin;
+    float* tout = P.t + (size_t)blockIdx.z * A.M * P.ldt;
+    const int umma_n = max(16, (min(kTsTM, A.M) + 15) & ~15);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTsStages; ++s) {
+            mbar_init(&full_a[s], kExpanders / 32);
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&tmem_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&wfull[s], 1);
+            mbar_init(&wempty[s], kExpanders / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s, tmem_a0 = tmem_base + 64u;  // accumulator: columns 0..63; A stages: 64.., 96..
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const CUtensorMap* wm = pi == 0 ? &wmap0 : (pi == 1 ? &wmap1 : &wmap2);
+            const int nslabs = (nchunks + 7) / 8;
+            auto issue_slab = [&](int j) {
+                if (j >= nslabs) return;
+                const int b = j & 1;
+                if (j >= 2) mbar_wait(&wempty[b], ((j >> 1) - 1) & 1);
+                mbar_expect_tx(&wfull[b], kTsSlabBytes);
+                tma_load_2d(sW + b * kTsSlabBytes, wm, (c_begin + j * 8) * 8, n0, &wfull[b]);
+            };
+            issue_slab(0);
+            issue_slab(1);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kTsStages, it = c / kTsStages;
+                if (c > 0 && (c & 7) == 0) issue_slab(c / 8 + 1);
+                if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+                mbar_expect_tx(&full_b[s], kTsBBytes);
+                tma_load_2d(sB + s * kTsBBytes, &xmap, (c_begin + c) * kChunkK, 0, &full_b[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, umma_n, A.bf16 != 0);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kTsStages, ph = (c / kTsStages) & 1;
+                mbar_wait(&full_a[s], ph);
+                mbar_wait(&full_b[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_addr = smem_u32(sB + s * kTsBBytes);
+#pragma unroll
+                for (int k = 0; k < kChunkK / 16; ++k)
+                    umma_f16_ts(tmem_base, tmem_a0 + (uint32_t)(s * 32 + k * 8), umma_desc_sw128(b_addr + k * 32), idesc,
+                                (c > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(&tmem_full);
+        }
+    } else {
+        // ===== expanders: warps 2..9; warp w reaches TMEM lanes (w % 4) * 32 .. + 31 = its weight rows; warps w and w + 4 share
+        // the rows and split a chunk's 64 columns (32 each = 16 TMEM columns)
+        const int quarter = warp & 3, qhalf = (warp - 2) >> 2;
+        const int e2 = threadIdx.x - 64;
+        const int row = quarter * 32 + lane;
+        const bool h_staged = nchunks * 8 <= 256;
+        if (h_staged) {
+            const uint4* hsrc = reinterpret_cast<const uint4*>(P.h + (size_t)c_begin * kChunkK);
+            for (int i = e2; i < nchunks * 8; i += kExpanders) h_stage[i] = __ldg(hsrc + i);
+            asm volatile("bar.sync 1, %0;" ::"n"(kExpanders) : "memory");
+        }
+        uint2 q0[8];
+        for (int cb = 0; cb < nchunks; cb += 8) {
+            {
+                const int j = cb >> 3, b = j & 1;
+                mbar_wait(&wfull[b], (j >> 1) & 1);
+                const uint4* rp = reinterpret_cast<const uint4*>(sW + b * kTsSlabBytes + row * 64);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = rp[i];
+                    q0[2 * i] = make_uint2(v.x, v.y);
+                    q0[2 * i + 1] = make_uint2(v.z, v.w);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&wempty[b]);
+            }
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                const int c = cb + ci;
+                if (c >= nchunks) break;
+                const int s = c % kTsStages, it = c / kTsStages;
+                const uint32_t wbits = qhalf ? q0[ci].y : q0[ci].x;  // this thread's 32 columns of the chunk
+                const uint4* hp = (h_staged ? h_stage + c * 8 : reinterpret_cast<const uint4*>(P.h + (size_t)(c_begin + c) * kChunkK)) + 4 * qhalf;
+                uint32_t o[16];
+#pragma unroll
+                for (int qi = 0; qi < 4; ++qi) {
+                    const uint4 hv = h_staged ? hp[qi] : __ldg(hp + qi);
+                    const uint32_t b8 = (wbits >> (8 * qi)) & 0xFFu;
+                    o[4 * qi + 0] = ((b8 * 0x40008000u) & 0x80008000u) ^ hv.x;
+                    o[4 * qi + 1] = ((b8 * 0x10002000u) & 0x80008000u) ^ hv.y;
+                    o[4 * qi + 2] = ((b8 * 0x04000800u) & 0x80008000u) ^ hv.z;
+                    o[4 * qi + 3] = ((b8 * 0x01000200u) & 0x80008000u) ^ hv.w;
+                }
+                if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);  // the MMAs that read this TMEM stage have completed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_a0 + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 32 + qhalf * 16);
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                    "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]),
+                    "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15])
+                    : "memory");
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_a[s]);
+            }
+        }
+        // ===== epilogue (warps 2..5 take token columns 0..31, warps 6..9 columns 32..63)
+        mbar_wait(&tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int n = n0 + row;
+        const float gs = (P.g != nullptr && n < P.N) ? to_f32(static_cast<const TP*>(P.g)[n]) : 1.f;
+        const int cb0 = 32 * qhalf;
+        if (cb0 < umma_n) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cb0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+                "%28,%29,%30,%31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (n < P.N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int m = cb0 + j;
+                    if (m < A.M) tout[(size_t)m * P.ldt + n] = __uint_as_float(v[j]) * gs;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
+}
+
 // x (bf16 / fp32) -> fp16 scratch, so that the TMA / MMA B operand is always fp16
 template <typename TX>
 __global__ void to_half_kernel(const TX* __restrict__ x, __half* __restrict__ y, int64_t n) {
@@ -524,8 +727,27 @@ int launch_tc5(const Tc5Launch& L, cudaStream_t s) {
     }
     dim3 grid((unsigned)tiles, (unsigned)((L.M + tile_m - 1) / tile_m), (unsigned)L.ksplit);
     ONEBIT_REQUIRE(grid.y <= 65535, "prefill_tc5: M too large (max 16.7M tokens)");
+    static int use_ts = -1;  // decode tile: A operand in tensor memory (tc5_decode_ts_kernel); ONEBIT_TC5_TS=0 keeps the shared-memory form
+    if (use_ts < 0) {
+        const char* e = getenv("ONEBIT_TC5_TS");
+        use_ts = (e && e[0] == '0') ? 0 : 1;
+    }
     return dispatch_dtype(L.param_dtype, [&](auto pt) {
         using TP = decltype(pt);
+        if (small && a.wtma && use_ts) {
+            auto kern = tc5_decode_ts_kernel<TP>;
+            static bool configured[64] = {false};
+            int dev = 0;
+            ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev >= 0 && dev < 64 && !configured[dev]) {
+                ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
+                ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                configured[dev] = true;
+            }
+            kern<<<grid, kThreads, kTsSmemBytes, s>>>(xmap, wm[0], wm[1], wm[2], a);
+            ONEBIT_CUDA_TRY(cudaGetLastError());
+            return (int)ONEBIT_OK;
+        }
         return small ? launch_inst<TP, 1, 64, false>(xmap, wm, a, grid, s) : launch_inst<TP, 2, 256, false>(xmap, wm, a, grid, s);
     });
 }
