@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "fused_gemv.cuh"
+#include "fused_gemv2.cuh"
 #include "imma_gemv.cuh"
 #include "p2p_allreduce.cuh"
 #include "prefill_attn.cuh"
@@ -269,6 +270,7 @@ struct AttnArgs {
     const float* stats_q; const float* stats_k; const float* stats_v; int ncta;  // per-CTA partials of each projection
     int M, H, n_heads, max_seq;   // H = row stride of t_q/t_k/t_v (local width under tensor parallelism)
     int n_ln, out_ld;            // rows of the FULL q/k/v layers (LayerNorm denominator); row stride of `out`
+    double inv_nln;              // 1 / n_ln (filled by the launcher)
     const int* pos;                 // [M] device
     const float* rope_cos; const float* rope_sin;  // [max_seq][kHeadDim/2]
     __half* kcache; __half* vcache; // [M_max][n_heads][max_seq][kHeadDim] for this layer
@@ -280,6 +282,7 @@ struct AttnArgs {
     int nsplit;
     float* part;                    // [M][n_heads][nsplit][kHeadDim + 2]
     int* tickets;                   // [M][n_heads], zero between launches
+    float* amax;                    // [M][n_heads] max |out| of every (sequence, head): quantiser bound of the o_proj stage, or nullptr
 };
 
 __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ AttnArgs A) {
@@ -314,14 +317,38 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     }
     float mq, rq, mk, rk, mv, rv;
     {
+        // every warp sums the per-CTA partials on its own (lane c takes CTAs c, c + 32, ...; all loads of a round of 160
+        // CTAs are issued before the first use; butterfly in fp64): no block barrier, no fp64 division on the chain
         double st[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        load_stat_partials(A.stats_q, A.ncta, A.M, m, st[0], st[1]);
-        load_stat_partials(A.stats_k, A.ncta, A.M, m, st[2], st[3]);
-        load_stat_partials(A.stats_v, A.ncta, A.M, m, st[4], st[5]);
-        block_reduce_sum<6>(st, shd);
-        finish_ln(st[0], st[1], A.n_ln, A.ln_eps, mq, rq);
-        finish_ln(st[2], st[3], A.n_ln, A.ln_eps, mk, rk);
-        finish_ln(st[4], st[5], A.n_ln, A.ln_eps, mv, rv);
+        const float* sp[3] = {A.stats_q, A.stats_k, A.stats_v};
+        for (int c0 = 0; c0 < A.ncta; c0 += 160) {
+            float2 p[3][5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int c = c0 + lane + 32 * i;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    p[j][i] = make_float2(0.f, 0.f);
+                    if (c < A.ncta) p[j][i] = *reinterpret_cast<const float2*>(sp[j] + ((size_t)c * A.M + m) * 2);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { st[2 * j] += (double)p[j][i].x; st[2 * j + 1] += (double)p[j][i].y; }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) st[j] = fused2::wsum(st[j]);
+        const double inv_n = A.inv_nln;
+        float* mo[3] = {&mq, &mk, &mv};
+        float* ro[3] = {&rq, &rk, &rv};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double mu = st[2 * j] * inv_n;
+            const double var = fma(-mu, mu, st[2 * j + 1] * inv_n);  // biased variance (nn.LayerNorm)
+            *mo[j] = (float)mu;
+            *ro[j] = rsqrtf(fmaxf((float)var, 0.f) + A.ln_eps);
+        }
     }
     const size_t col = (size_t)m * A.H + hd * kHeadDim;
     const int half = kHeadDim / 2, dp = d < half ? d + half : d - half, fi = d < half ? d : d - half;
@@ -415,7 +442,14 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
 #pragma unroll
     for (int w = 0; w < NW; ++w) acc += sc[w * kHeadDim + d];
     if (nsplit == 1) {
-        A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = acc * inv;
+        const float o = acc * inv;
+        A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = o;
+        if (A.amax != nullptr) {
+            const float wm = fused2::wmax(fabsf(o));
+            if (lane == 0) red[warp] = wm;  // (last read of red was before two barriers)
+            __syncthreads();
+            if (d == 0) A.amax[m * A.n_heads + hd] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+        }
         return;
     }
     // ---- split-KV: publish this slice's (max, sum, numerator); the last slice to arrive merges all of them in slice order
@@ -439,7 +473,14 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
         den += __ldcg(base + z * (kHeadDim + 2) + 1) * f;
         num += __ldcg(base + z * (kHeadDim + 2) + 2 + d) * f;
     }
-    A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = num / den;
+    const float o = num / den;
+    A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = o;
+    if (A.amax != nullptr) {
+        const float wm = fused2::wmax(fabsf(o));
+        if (lane == 0) red[warp] = wm;
+        __syncthreads();
+        if (d == 0) A.amax[m * A.n_heads + hd] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    }
     if (d == 0) A.tickets[m * A.n_heads + hd] = 0;
 }
 
@@ -657,6 +698,14 @@ struct onebit_decoder {
     // host-side upper bound of every sequence's position (reset value + steps enqueued): a step that could write past
     // max_seq_len is refused instead of overrunning the KV cache
     int pos_hi = 0;
+    // second-generation fused stages (fused_gemv2.cuh; tp == 1): fp32 side tables in quantiser-item order
+    // [L][7] (q k v o gate up down): static input factors (RMSNorm weight folded in for q/k/v/gate/up), weight scales
+    bool v2 = false;
+    float* tab_store = nullptr;
+    std::vector<const float*> tab_fp, tab_g32;
+    std::vector<float> tab_fmax;
+    float *ext_qkv = nullptr, *ext_o = nullptr, *ext_gu = nullptr, *ext_d = nullptr;  // extension records of the producers
+    float* attn_amax = nullptr;  // [max_batch][heads]
 };
 
 namespace {
@@ -777,6 +826,11 @@ int fused_launch(fused::Args a, int param_dtype, cudaStream_t s, int* ctas_per_p
     });
 }
 
+int launch_attn(dim3 grid, dim3 block, size_t smem, cudaStream_t s, AttnArgs at) {
+    at.inv_nln = 1.0 / (double)at.n_ln;
+    return launch_pdl(attn_kernel, grid, block, smem, s, at);
+}
+
 int allreduce(const onebit_decoder* D, float* data, int64_t count, cudaStream_t s) {
     if (D->tp <= 1) return ONEBIT_OK;
     if (D->p2p_on) return p2p_allreduce(D->p2p, data, count, s);
@@ -838,7 +892,7 @@ int run_fused_layers(onebit_decoder* D, int M, cudaStream_t s, bool with_attenti
             at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
             at.out = D->attn_out; at.ln_eps = C.ln_eps;
             const size_t asmem = attn_finish_args(D, at, M, false);
-            rc = launch_pdl(attn_kernel, dim3(M, D->heads_l, at.nsplit), dim3(kHeadDim), asmem, s, at);
+            rc = launch_attn( dim3(M, D->heads_l, at.nsplit), dim3(kHeadDim), asmem, s, at);
             if (rc) return rc; ++*launches;
         }
         // ---- stage 3: attention output -> o_proj (row-parallel: local K slice, zero-padded to a multiple of 256)
@@ -880,6 +934,228 @@ int run_fused_layers(onebit_decoder* D, int M, cudaStream_t s, bool with_attenti
         f5.p[0].h = P.down.input_factor; f5.p[0].t = D->t_d; f5.p[0].stats = D->st_d; f5.p[0].n_rows = H; f5.p[0].ld_t = H;
         rc = fused_launch(f5, pd, s, &nc_d); if (rc) return rc; ++*launches;
         rc = allreduce(D, D->t_d, (int64_t)M * H, s); if (rc) return rc;
+    }
+    *cur_io = cur;
+    *nc_d_io = nc_d;
+    return ONEBIT_OK;
+}
+
+// ---- second-generation fused stage (fused_gemv2.cuh) -------------------------------------------------------
+bool fused2_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ONEBIT_FUSED_V2");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// 256 threads: two CTAs per SM (this stage's and the next one's), half of the shared memory each; 512 threads: one CTA per SM
+int fused2_threads() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ONEBIT_FUSED2_THREADS");
+        v = (e && atoi(e) == 256) ? 256 : 512;
+    }
+    return v;
+}
+size_t fused2_smem_cap() { return fused2_threads() == 256 ? 110 * 1024 : 224 * 1024; }
+
+int fused2_rows_per_cta(int total_rows, int M, int K) {
+    const int sms = num_sms(), th = fused2_threads();
+    int rows = ((total_rows + sms - 1) / sms + 31) / 32 * 32;
+    if (rows < 32) rows = 32;
+    if (rows > 192) rows = 192;
+    if (M > 2) return 0;
+    while (rows > 32 && fused2::smem_bytes(M, K, rows, th) > fused2_smem_cap()) rows -= 32;
+    if (fused2::smem_bytes(M, K, rows, th) > fused2_smem_cap()) return 0;
+    return rows;
+}
+
+template <int TILES, int THREADS>
+int fused2_launch_inst2(const fused2::Args& a, int ctas, cudaStream_t s) {
+    auto kern = fused2::fused_gemv2_kernel<TILES, THREADS>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_cap()));
+        ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured[dev] = true;
+    }
+    return launch_pdl(kern, dim3(ctas), dim3(THREADS), fused2::smem_bytes(a.M, a.K, a.rows_per_cta, THREADS), s, a);
+}
+template <int TILES>
+int fused2_launch_inst(const fused2::Args& a, int ctas, cudaStream_t s) {
+    return fused2_threads() == 256 ? fused2_launch_inst2<TILES, 256>(a, ctas, s) : fused2_launch_inst2<TILES, 512>(a, ctas, s);
+}
+
+int fused2_launch(fused2::Args a, int ext_rep_stride, cudaStream_t s, int* ctas_per_problem) {
+    a.ext_rep_stride = ext_rep_stride;
+    a.inv_k = 1.0 / (double)a.K;
+    a.inv_nln = 1.0 / (double)(a.n_ln > 0 ? a.n_ln : a.K);
+    int ctas = 0;
+    for (int i = 0; i < a.nprob; ++i) {
+        a.p[i].cta_begin = ctas;
+        ctas += (a.p[i].n_rows + a.rows_per_cta - 1) / a.rows_per_cta;
+    }
+    *ctas_per_problem = (a.p[0].n_rows + a.rows_per_cta - 1) / a.rows_per_cta;
+    static int dup = -1;  // experiment: every stage twice (idempotent) — does the second launch find the code in the I-cache?
+    if (dup < 0) { const char* e = getenv("ONEBIT_DUP_STAGE"); dup = e ? atoi(e) : 0; }
+    if (dup > 0 && a.mode != fused::EMBED_NORM) {
+        fused2::Args b = a;
+        b.trace = 0;
+        int rc = ONEBIT_OK;
+        switch (a.rows_per_cta / 16) {
+            case 2: rc = fused2_launch_inst<2>(b, ctas, s); break;
+            case 6: rc = fused2_launch_inst<6>(b, ctas, s); break;
+            case 10: rc = fused2_launch_inst<10>(b, ctas, s); break;
+            default: break;
+        }
+        if (rc) return rc;
+    }
+    switch (a.rows_per_cta / 16) {
+        case 2: return fused2_launch_inst<2>(a, ctas, s);
+        case 4: return fused2_launch_inst<4>(a, ctas, s);
+        case 6: return fused2_launch_inst<6>(a, ctas, s);
+        case 8: return fused2_launch_inst<8>(a, ctas, s);
+        case 10: return fused2_launch_inst<10>(a, ctas, s);
+        case 12: return fused2_launch_inst<12>(a, ctas, s);
+        default: return fail(ONEBIT_ERR_INVALID_ARGUMENT, "fused stage: unsupported rows per CTA");
+    }
+}
+
+int build_v2_tables(onebit_decoder* D) {
+    const onebit_decoder_config& C = D->cfg;
+    const int H = C.hidden_size, I = C.intermediate_size, L = C.num_layers;
+    const size_t per_layer = (size_t)(3 * H + H + 2 * H + I) + (size_t)(3 * H + H + 2 * I + H);
+    ONEBIT_CUDA_TRY(cudaMalloc(&D->tab_store, (per_layer * L + (size_t)7 * L) * sizeof(float)));
+    float* fm_dev = D->tab_store + per_layer * L;
+    D->tab_fp.resize((size_t)L * 7);
+    D->tab_g32.resize((size_t)L * 7);
+    D->tab_fmax.resize((size_t)L * 7);
+    float* p = D->tab_store;
+    const int rc = dispatch_dtype(C.param_dtype, [&](auto pt) {
+        using TP = decltype(pt);
+        for (int l = 0; l < L; ++l) {
+            const onebit_layer_params& P = D->layers[l];
+            const onebit_bitlinear_params* bl[7] = {&P.q, &P.k, &P.v, &P.o, &P.gate, &P.up, &P.down};
+            fused2::TableJobs J = {};
+            for (int i = 0; i < 7; ++i) {
+                fused2::TableJob& T = J.j[i];
+                T.k = i == 6 ? I : H;
+                T.n = (i == 4 || i == 5) ? I : H;
+                T.h = bl[i]->input_factor;
+                T.lnw = i < 3 ? P.input_layernorm : ((i == 4 || i == 5) ? P.post_attention_layernorm : nullptr);
+                T.g = bl[i]->weight_scale;
+                T.fp = p; p += T.k;
+                T.g32 = p; p += T.n;
+                T.fmax = fm_dev + (size_t)l * 7 + i;
+                D->tab_fp[(size_t)l * 7 + i] = T.fp;
+                D->tab_g32[(size_t)l * 7 + i] = T.g32;
+            }
+            fused2::side_tables_kernel<TP><<<7, 1024>>>(J);
+        }
+        return (int)ONEBIT_OK;
+    });
+    if (rc) return rc;
+    ONEBIT_CUDA_TRY(cudaGetLastError());
+    ONEBIT_CUDA_TRY(cudaMemcpy(D->tab_fmax.data(), fm_dev, (size_t)7 * L * sizeof(float), cudaMemcpyDeviceToHost));
+    return ONEBIT_OK;
+}
+
+// The layer loop on the second-generation stages (tp == 1): same 5 launches per layer as run_fused_layers, but every
+// stage's prologue takes its scalars from the producer's records (fused_gemv2.cuh).
+int run_fused2_layers(onebit_decoder* D, int M, cudaStream_t s, bool with_attention, bool first_is_embed, int* launches,
+                      int* cur_io, int* nc_d_io, bool* ok) {
+    const onebit_decoder_config& C = D->cfg;
+    const int H = C.hidden_size, I = C.intermediate_size, B = C.max_batch;
+    const int uH = H / imma::kUnitCols, uI = I / imma::kUnitCols;
+    const int cH = (H + imma::kRows - 1) / imma::kRows, cI = (I + imma::kRows - 1) / imma::kRows;
+    const int rq = fused2_rows_per_cta(3 * H, M, H), ro = fused2_rows_per_cta(H, M, H);
+    const int rg = fused2_rows_per_cta(2 * I, M, H), rd = fused2_rows_per_cta(H, M, I);
+    *ok = D->v2 && fused_enabled() && fused2_enabled() && rq && ro && rg && rd;
+    if (!*ok) return ONEBIT_OK;
+    int cur = *cur_io, nc_d = *nc_d_io, rc;
+    const char* tre = getenv("ONEBIT_TRACE_STAGE");  // (trace builds) which stage of the last layer records its clocks: 1, 3, 4, 5
+    const int trace_stage = tre ? atoi(tre) : 5;
+    const int ext_rep = (5 * cH + 2 * cI) * B * fused2::kExt;  // floats of one replica of the record block
+    auto set_problem = [&](fused2::Problem& p, int l, int i, const onebit_bitlinear_params& bp, float* t, float* stats, float* ext,
+                           int n_rows) {
+        p.w = reinterpret_cast<const uint8_t*>(bp.weight);
+        p.g32 = D->tab_g32[(size_t)l * 7 + i];
+        p.fp = D->tab_fp[(size_t)l * 7 + i];
+        p.fmax = D->tab_fmax[(size_t)l * 7 + i];
+        p.t = t; p.stats = stats; p.ext = ext; p.n_rows = n_rows; p.ld_t = n_rows;
+    };
+    for (int l = 0; l < C.num_layers; ++l) {
+        const onebit_layer_params& P = D->layers[l];
+        int nc_q = 0, nc_o = 0, nc_g = 0;
+        // ---- stage 1: (embed | resid + LN(down)) -> RMSNorm -> q,k,v
+        fused2::Args f = {};
+        f.nprob = 3; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rq;
+        f.mode = (l == 0 && first_is_embed) ? fused::EMBED_NORM : fused::RESID_NORM;
+        f.t_a = D->t_d; f.stats_a = D->st_d; f.ext_a = D->ext_d; f.ncta_a = nc_d;
+        f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1];
+        f.embed = D->embed; f.ids = D->ids; f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
+        const onebit_bitlinear_params* qkv[3] = {&P.q, &P.k, &P.v};
+        for (int i = 0; i < 3; ++i)
+            set_problem(f.p[i], l, i, *qkv[i], D->t_qkv + (size_t)i * B * H, D->st_qkv + (size_t)i * cH * B * 2,
+                        D->ext_qkv + (size_t)i * cH * B * fused2::kExt, H);
+        f.ext_stride_in = f.ext_stride_out = cH * B * 4;
+        f.a_perm = 1; f.rin_perm = 1; f.rout_perm = 1; f.t_perm = 0;  // q/k/v feed the attention kernel: natural order
+        f.trace = l == C.num_layers - 1 && trace_stage == 1;
+        rc = fused2_launch(f, ext_rep, s, &nc_q); if (rc) return rc; ++*launches;
+        cur ^= 1;
+        // ---- stage 2: attention (also records max |out| per head for the o_proj quantiser)
+        if (with_attention) {
+            AttnArgs at = {};
+            at.t_q = f.p[0].t; at.t_k = f.p[1].t; at.t_v = f.p[2].t;
+            at.stats_q = f.p[0].stats; at.stats_k = f.p[1].stats; at.stats_v = f.p[2].stats; at.ncta = nc_q;
+            at.M = M; at.H = H; at.n_ln = H; at.out_ld = H; at.n_heads = C.num_heads; at.max_seq = C.max_seq_len;
+            at.pos = D->pos; at.rope_cos = D->rope_cos; at.rope_sin = D->rope_sin;
+            const size_t layer_cache = (size_t)B * C.num_heads * C.max_seq_len * kHeadDim;
+            at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
+            at.out = D->attn_out; at.ln_eps = C.ln_eps; at.amax = D->attn_amax;
+            const size_t asmem = attn_finish_args(D, at, M, false);
+            rc = launch_attn( dim3(M, C.num_heads, at.nsplit), dim3(kHeadDim), asmem, s, at);
+            if (rc) return rc; ++*launches;
+        }
+        // ---- stage 3: attention output -> o_proj; its records carry the residual terms for stage 4
+        f = {};
+        f.nprob = 1; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = ro; f.mode = fused::PLAIN; f.x_plain = D->attn_out;
+        if (with_attention) { f.x_amax = D->attn_amax; f.n_amax = C.num_heads; }
+        f.resid_next = D->resid[cur]; f.resid_ld = H; f.ext_stride_out = cH * B * 4;
+        set_problem(f.p[0], l, 3, P.o, D->t_o, D->st_o, D->ext_o, H);
+        f.rnext_perm = 1; f.t_perm = 1;
+        f.trace = l == C.num_layers - 1 && trace_stage == 3;
+        rc = fused2_launch(f, ext_rep, s, &nc_o); if (rc) return rc; ++*launches;
+        // ---- stage 4: resid + LN(o) -> RMSNorm -> gate, up
+        f = {};
+        f.nprob = 2; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = rg; f.mode = fused::RESID_NORM;
+        f.t_a = D->t_o; f.stats_a = D->st_o; f.ext_a = D->ext_o; f.ncta_a = nc_o;
+        f.resid_in = D->resid[cur]; f.resid_out = D->resid[cur ^ 1]; f.ln_eps = C.ln_eps; f.rms_eps = C.rms_eps;
+        const onebit_bitlinear_params* gu[2] = {&P.gate, &P.up};
+        for (int i = 0; i < 2; ++i)
+            set_problem(f.p[i], l, 4 + i, *gu[i], D->t_gu + (size_t)i * B * I, D->st_gu + (size_t)i * cI * B * 2,
+                        D->ext_gu + (size_t)i * cI * B * fused2::kExt, I);
+        f.ext_stride_in = cH * B * 4; f.ext_stride_out = cI * B * 4;
+        const int last = l == C.num_layers - 1;  // the final glue kernel reads the residual stream and t_d in natural order
+        f.a_perm = 1; f.rin_perm = 1; f.rout_perm = !last; f.t_perm = 1;
+        f.trace = l == C.num_layers - 1 && trace_stage == 4;
+        rc = fused2_launch(f, ext_rep, s, &nc_g); if (rc) return rc; ++*launches;
+        cur ^= 1;
+        // ---- stage 5: silu(LN(gate)) * LN(up) -> down_proj; records carry the residual terms for the next layer
+        fused2::Args f5 = {};
+        f5.nprob = 1; f5.M = M; f5.K = I; f5.units = uI; f5.rows_per_cta = rd; f5.mode = fused::SILU_MUL;
+        f5.t_a = f.p[0].t; f5.stats_a = f.p[0].stats; f5.ext_a = f.p[0].ext; f5.ncta_a = nc_g;
+        f5.t_b = f.p[1].t; f5.stats_b = f.p[1].stats; f5.ext_b = f.p[1].ext; f5.ncta_b = nc_g;
+        f5.ln_eps = C.ln_eps; f5.n_ln = I;
+        f5.resid_next = D->resid[cur]; f5.resid_ld = H; f5.ext_stride_out = cH * B * 4;
+        set_problem(f5.p[0], l, 6, P.down, D->t_d, D->st_d, D->ext_d, H);
+        f5.a_perm = 1; f5.rnext_perm = !last; f5.t_perm = !last;
+        f5.trace = l == C.num_layers - 1 && trace_stage == 5;
+        rc = fused2_launch(f5, ext_rep, s, &nc_d); if (rc) return rc; ++*launches;
     }
     *cur_io = cur;
     *nc_d_io = nc_d;
@@ -952,7 +1228,7 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         at.out = D->attn_out; at.ln_eps = C.ln_eps;
         const size_t asmem = attn_finish_args(D, at, M, true);
         if (!only_proj) {
-            rc = launch_pdl(attn_kernel, dim3(M, D->heads_l, at.nsplit), dim3(kHeadDim), asmem, s, at);
+            rc = launch_attn( dim3(M, D->heads_l, at.nsplit), dim3(kHeadDim), asmem, s, at);
             if (rc) return rc; ++*launches;
         }
         // ---- glue 2: attention output [M][Hk] (pad columns stay zero) -> fp16
@@ -1017,6 +1293,7 @@ void onebit_decoder_destroy(onebit_decoder* D) {
     cudaFree(D->p2p_state);
     cudaFree(D->pf_ws);
     cudaFree(D->pf_h16_store);
+    cudaFree(D->tab_store);
     cudaFree(D->arena);
     delete D;
 }
@@ -1086,6 +1363,12 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     D->attn_nsplit = std::max(1, std::min(16, cfg->max_seq_len / 512));
     const size_t o_ap = take((size_t)B * D->heads_l * D->attn_nsplit * (kHeadDim + 2) * 4), o_at = take((size_t)B * D->heads_l * 4);
     const size_t o_xI = take(big ? (size_t)B * std::max(I, D->Ik) * 2 : 16);
+    // record arrays of the second-generation fused stages: one contiguous block, fused2::kReplicas copies of it
+    const size_t ext_one = ((size_t)5 * cH + (size_t)2 * cI) * B * fused2::kExt * 4;
+    const size_t o_eq = take(ext_one * fused2::kReplicas);
+    const size_t o_eo = o_eq + (size_t)3 * cH * B * fused2::kExt * 4, o_eg = o_eo + (size_t)cH * B * fused2::kExt * 4;
+    const size_t o_ed = o_eg + (size_t)2 * cI * B * fused2::kExt * 4;
+    const size_t o_am = take((size_t)B * cfg->num_heads * 4);
     const bool need_h16 = big && cfg->param_dtype != ONEBIT_F16;
     const size_t o_h16 = take(need_h16 ? (size_t)L * (5 * (size_t)H + D->Hk + D->Ik) * 2 : 16);
     cudaError_t e = cudaMalloc(&D->arena, off);
@@ -1108,6 +1391,13 @@ int onebit_decoder_create(onebit_decoder** out, const onebit_decoder_config* cfg
     D->red_o = (float*)(a + o_ro); D->red_d = (float*)(a + o_rd);
     D->attn_part = (float*)(a + o_ap); D->attn_tickets = (int*)(a + o_at);
     D->xI_f16 = (__half*)(a + o_xI);
+    D->ext_qkv = (float*)(a + o_eq); D->ext_o = (float*)(a + o_eo); D->ext_gu = (float*)(a + o_eg); D->ext_d = (float*)(a + o_ed);
+    D->attn_amax = (float*)(a + o_am);
+    if (tp == 1) {
+        const int rc = build_v2_tables(D);
+        if (rc != ONEBIT_OK) { onebit_decoder_destroy(D); return rc; }
+        D->v2 = true;
+    }
     D->h16_store = (__half*)(a + o_h16);
     if (big) {  // the tcgen05 A operand folds input_factor in as fp16: one-time copies when the parameters are bf16 / fp32
         D->h16.resize((size_t)L * 7);
@@ -1217,8 +1507,12 @@ static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced
         if (rc) return rc;
         use_fused = true;  // (skips the split-chain loop below)
     } else {
-        rc = run_fused_layers(D, M, s, /*with_attention=*/true, /*first_is_embed=*/true, &launches, &cur, &nc_d, &use_fused);
+        rc = run_fused2_layers(D, M, s, /*with_attention=*/true, /*first_is_embed=*/true, &launches, &cur, &nc_d, &use_fused);
         if (rc) return rc;
+        if (!use_fused) {
+            rc = run_fused_layers(D, M, s, /*with_attention=*/true, /*first_is_embed=*/true, &launches, &cur, &nc_d, &use_fused);
+            if (rc) return rc;
+        }
     }
     if (!use_fused && D->tp > 1)
         return fail(ONEBIT_ERR_INVALID_ARGUMENT, "tensor-parallel decode needs the fused stages (batch <= 2, ONEBIT_FUSED != 0) or a decoder created with max_batch > 4 (batched tcgen05 path)");
@@ -1257,7 +1551,7 @@ static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced
         at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
         at.out = D->attn_out; at.ln_eps = C.ln_eps;
         const size_t asmem2 = attn_finish_args(D, at, M, false);
-        rc = launch_pdl(attn_kernel, dim3(M, C.num_heads, at.nsplit), dim3(kHeadDim), asmem2, s, at);
+        rc = launch_attn( dim3(M, C.num_heads, at.nsplit), dim3(kHeadDim), asmem2, s, at);
         if (rc) return rc; ++launches;
         // ---- glue 2: attention output -> o digits
         g = {};
@@ -1527,7 +1821,10 @@ int onebit_decoder_gemv_only(onebit_decoder* D, int batch, void* stream) {
     {
         int launches = 0, cur = 0, nc_d = cH;
         bool used = false;
-        int rc = run_fused_layers(D, M, s, /*with_attention=*/false, /*first_is_embed=*/false, &launches, &cur, &nc_d, &used);
+        int rc = run_fused2_layers(D, M, s, /*with_attention=*/false, /*first_is_embed=*/false, &launches, &cur, &nc_d, &used);
+        if (rc) return rc;
+        if (used) return ONEBIT_OK;
+        rc = run_fused_layers(D, M, s, /*with_attention=*/false, /*first_is_embed=*/false, &launches, &cur, &nc_d, &used);
         if (rc) return rc;
         if (used) return ONEBIT_OK;
     }
@@ -1632,6 +1929,14 @@ extern "C" __attribute__((visibility("default"))) int onebit_debug_read_trace_de
     return cudaMemcpyFromSymbol(out8, onebit::imma::g_trace, sizeof(long long) * 8) == cudaSuccess ? 0 : -2;
 #else
     (void)out8;
+    return -1;
+#endif
+}
+extern "C" __attribute__((visibility("default"))) int onebit_debug_read_trace16(long long* out16) {
+#ifdef ONEBIT_TRACE
+    return cudaMemcpyFromSymbol(out16, onebit::imma::g_trace, sizeof(long long) * 16) == cudaSuccess ? 0 : -2;
+#else
+    (void)out16;
     return -1;
 #endif
 }

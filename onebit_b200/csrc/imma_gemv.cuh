@@ -36,7 +36,7 @@ namespace onebit {
 namespace imma {
 
 #ifdef ONEBIT_TRACE
-__device__ long long g_trace[8];
+__device__ long long g_trace[16];
 #define TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) ::onebit::imma::g_trace[i] = clock64(); } while (0)
 #else
 #define TR(i)
