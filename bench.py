@@ -274,12 +274,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if B > 4:
             kname = ("prefill_tc5_kernel<decode tile> (tcgen05.mma kind::f16, packed signs expanded in registers with "
                      "input_factor folded in, TMA activations, split-K; one launch per projection group)")
+        elif os.environ.get("ONEBIT_FUSED", "1") != "0" and os.environ.get("ONEBIT_FUSED_V2", "1") != "0" and B <= 2:
+            kname = ("fused2::fused_gemv2_kernel (glue prologue from the producer's records, no block reduction + bit-plane "
+                     "IMMA packed-sign GEMV, one launch per BitLinear group)")
         elif os.environ.get("ONEBIT_FUSED", "1") != "0":
             kname = "fused::fused_gemv_kernel (glue prologue + bit-plane IMMA packed-sign GEMV, one launch per BitLinear group)"
         else:
             kname = "imma::gemv_kernel (bit-plane IMMA packed-sign GEMV)"
         traffic = None
-        tpath = ROOT / "profiles" / "r01_gemv_traffic.json"
+        tpath = ROOT / "profiles" / ("r02_fused2_traffic.json" if "fused2" in kname else "r01_gemv_traffic.json")
         if tpath.exists() and B <= 4:
             traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
         out["roofline"] = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",

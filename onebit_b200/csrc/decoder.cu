@@ -1124,7 +1124,8 @@ int run_fused2_layers(onebit_decoder* D, int M, cudaStream_t s, bool with_attent
         // ---- stage 3: attention output -> o_proj; its records carry the residual terms for stage 4
         f = {};
         f.nprob = 1; f.M = M; f.K = H; f.units = uH; f.rows_per_cta = ro; f.mode = fused::PLAIN; f.x_plain = D->attn_out;
-        if (with_attention) { f.x_amax = D->attn_amax; f.n_amax = C.num_heads; }
+        // (without attention — the projection-only timing chain — the records are those of the last real step: stale but valid)
+        f.x_amax = D->attn_amax; f.n_amax = C.num_heads;
         f.resid_next = D->resid[cur]; f.resid_ld = H; f.ext_stride_out = cH * B * 4;
         set_problem(f.p[0], l, 3, P.o, D->t_o, D->st_o, D->ext_o, H);
         f.rnext_perm = 1; f.t_perm = 1;

@@ -21,7 +21,9 @@ namespace fused {
 using imma::QMeta;
 constexpr int kThreads = 512;
 constexpr int kWarps = 16;
-constexpr int kRowPad = 32;  // bytes of padding per weight row in shared memory (LDS.64 of 8 rows x 4 lanes: 2 wavefronts)
+// bytes of padding per weight row in shared memory: pitch = 32 bytes past a multiple of 128, so that the LDS.64 of 8 rows x
+// 4 lanes covers all 32 banks (2 wavefronts) at every K (a fixed 32-byte pad does that for K = 4096 only)
+__host__ __device__ inline int row_pad(int kb) { return (32 - (kb & 127) + 128) & 127; }
 
 // shared-memory staging of x' is padded by 8 floats per 32 so that the quantiser's stride-8 gathers are conflict-free
 __host__ __device__ inline int xs_pad(int k) { return k + ((k >> 5) << 3); }
@@ -56,7 +58,7 @@ struct Args {
 };
 
 inline size_t smem_bytes(int M, int K, int rows_per_cta) {
-    const size_t wbytes = (size_t)rows_per_cta * (K / 8 + kRowPad);
+    const size_t wbytes = (size_t)rows_per_cta * (K / 8 + row_pad(K / 8));
     const size_t dig = (size_t)M * (K / 256) * 4 * kDigBlk;
     const size_t xs = (size_t)xs_pad(K) * 4 + 64;
     const size_t red = (size_t)kWarps * rows_per_cta * 8 * 4;  // aliases the weight region after the main loop
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemv_kernel(const __grid_co
     __shared__ double s_invd[2 * NT];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
-    const int M = A.M, K = A.K, K4 = K >> 2, Kb = K >> 3, pitch = Kb + kRowPad;
+    const int M = A.M, K = A.K, K4 = K >> 2, Kb = K >> 3, pitch = Kb + row_pad(Kb);
     constexpr int kRowsCta = TILES * 16;
     int pi = 0;
 #pragma unroll

@@ -30,7 +30,6 @@ namespace onebit {
 namespace fused2 {
 
 using fused::kDigBlk;
-using fused::kRowPad;
 using fused::EMBED_NORM;
 using fused::PLAIN;
 using fused::RESID_NORM;
@@ -93,8 +92,10 @@ __device__ __forceinline__ void finish_ln_fast(float s, float q, double inv_n, f
 #define TR2(i)
 #endif
 
+using fused::row_pad;  // K = 11008 (1376 bytes per row) with a fixed 32-byte pad landed every row on the same banks
+
 inline size_t smem_bytes(int M, int K, int rows_per_cta, int threads) {
-    const size_t wbytes = (size_t)rows_per_cta * (K / 8 + kRowPad);
+    const size_t wbytes = (size_t)rows_per_cta * (K / 8 + row_pad(K / 8));
     const size_t red = (size_t)(threads / 32) * rows_per_cta * 8 * 4;  // aliases the weight region after the main loop
     const size_t dig = (size_t)M * (K / 256) * 4 * kDigBlk;
     return (((wbytes > red ? wbytes : red) + 15) & ~(size_t)15) + dig + 64;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
     }
     __syncthreads();  // sA complete (everything below reads the shared copy)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
-    const int M = A.M, K = A.K, Kb = K >> 3, pitch = Kb + kRowPad;
+    const int M = A.M, K = A.K, Kb = K >> 3, pitch = Kb + row_pad(Kb);
     constexpr int kRowsCta = TILES * 16;
     int pi = 0;
 #pragma unroll
@@ -201,6 +202,20 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
     }
     for (int it = kItems * kThreads + tid; it < items; it += 8 * kThreads)  // one 128-byte line per 8 items
         asm volatile("prefetch.global.L2 [%0];" ::"l"(fp4 + (it & ~7)));
+    // everything the glue needs that does not depend on the producer: resolved before the wait
+    const int mode = A.mode;
+    const bool norm_mode = mode == EMBED_NORM || mode == RESID_NORM;
+    const bool has_rec = mode == RESID_NORM || mode == SILU_MUL;
+    const bool silu = mode == SILU_MUL;
+    const float* a_base = mode == PLAIN ? A.x_plain : A.t_a;
+    const float* b_base = mode == RESID_NORM ? A.resid_in : (silu ? A.t_b : nullptr);
+    const bool a_perm = A.a_perm != 0, b_perm = (mode == RESID_NORM ? A.rin_perm : A.a_perm) != 0;
+    // every record array exists kReplicas times: 128+ CTAs polling the same few L2 lines serialise on their slices
+    const size_t rep_off = (size_t)(blockIdx.x & (kReplicas - 1)) * A.ext_rep_stride;
+    const float4* rec_a = reinterpret_cast<const float4*>(A.ext_a + rep_off) + (size_t)lane * M;
+    const float4* rec_b = reinterpret_cast<const float4*>((silu ? A.ext_b : A.ext_a + A.ext_stride_in) + rep_off) + (size_t)lane * M;
+    const int n_a = A.ncta_a, n_b = silu ? A.ncta_b : A.ncta_a;
+    const int qmul = (tid & 7) == 7 ? -1 : (1 << (7 - (tid & 7)));  // plane scale of this thread's items (j = tid % 8)
     imma::pdl_launch_dependents();
     TR2(12);
     imma::pdl_wait();
@@ -215,17 +230,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
 
     // ---- 2. glue, per token: round 0 of the vector loads goes in flight, warp 0 turns the producer's records into the
     //         stage scalars (one barrier), then rounds of (x', quantise) with the next round's loads in flight ----
-    const int mode = A.mode;
-    const bool norm_mode = mode == EMBED_NORM || mode == RESID_NORM;
-    // every record array exists kReplicas times: 128+ CTAs polling the same few L2 lines serialise on their slices
-    const size_t rep_off = (size_t)(blockIdx.x & (kReplicas - 1)) * A.ext_rep_stride;
     struct Rnd { float va[kItems][4], vb[kItems][4]; float4 fv[kItems]; };
     for (int m = 0; m < M; ++m) {
-        const float* a32 = (mode == PLAIN ? A.x_plain : A.t_a) + (size_t)m * K;
+        const float* a32 = a_base + (size_t)m * K;
         const unsigned short* erow =
             mode == EMBED_NORM ? reinterpret_cast<const unsigned short*>(A.embed + (size_t)A.ids[m] * K) : nullptr;
-        const float* b32 = mode == RESID_NORM ? A.resid_in + (size_t)m * K : (mode == SILU_MUL ? A.t_b + (size_t)m * K : nullptr);
-        const bool b_perm = mode == RESID_NORM ? A.rin_perm : A.a_perm;
+        const float* b32 = b_base ? b_base + (size_t)m * K : nullptr;
         auto load_round = [&](int rd, Rnd& R) {
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
@@ -238,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
                     if (erow) {
 #pragma unroll
                         for (int b = 0; b < 4; ++b) R.va[i][b] = __uint_as_float((uint32_t)erow[c0 + 8 * b]);  // raw fp16 bits
-                    } else if (A.a_perm) {
+                    } else if (a_perm) {
                         const float4 v = reinterpret_cast<const float4*>(a32)[it];
                         R.va[i][0] = v.x; R.va[i][1] = v.y; R.va[i][2] = v.z; R.va[i][3] = v.w;
                     } else {
@@ -263,19 +273,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
         for (int i = 0; i < kItems; ++i) cur.fv[i] = fv0[i];
         TR2(8);
         float mean_a = 0.f, rstd_a = 1.f, mean_b = 0.f, rstd_b = 1.f, bound = 0.f, rr = 1.f;
-        const bool has_rec = mode == RESID_NORM || mode == SILU_MUL;
         if (has_rec || (mode == PLAIN && A.x_amax != nullptr)) {
             // every warp reduces the records on its own (no barrier: measured faster than one warp + broadcast)
             {
                 if (has_rec) {
                     // acc_a = (sum t, sum t^2, max t, min t) of producer A; acc_b = RESID: (sum r t, sum r, sum r^2, max |r|),
                     // SILU: the base record of producer B. All loads of a round are issued before the first use.
-                    const bool silu = mode == SILU_MUL;
                     float aa[4] = {0.f, 0.f, -INFINITY, INFINITY};
                     float ab[4] = {0.f, 0.f, silu ? -INFINITY : 0.f, silu ? INFINITY : 0.f};
-                    const float4* base_a = reinterpret_cast<const float4*>(A.ext_a + rep_off);
-                    const float4* second = reinterpret_cast<const float4*>((silu ? A.ext_b : A.ext_a + A.ext_stride_in) + rep_off);
-                    const int n_a = A.ncta_a, n_b = silu ? A.ncta_b : A.ncta_a;
                     for (int c0 = 0; c0 < max(n_a, n_b); c0 += 32 * kRecLanes) {
                         float4 ra[kRecLanes], rb[kRecLanes];
 #pragma unroll
@@ -283,8 +288,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
                             const int c = c0 + lane + 32 * i;
                             ra[i] = make_float4(0.f, 0.f, -INFINITY, INFINITY);
                             rb[i] = make_float4(0.f, 0.f, silu ? -INFINITY : 0.f, silu ? INFINITY : 0.f);
-                            if (c < n_a) ra[i] = base_a[(size_t)c * M + m];
-                            if (c < n_b) rb[i] = second[(size_t)c * M + m];
+                            if (c < n_a) ra[i] = rec_a[(size_t)(c0 + 32 * i) * M + m];
+                            if (c < n_b) rb[i] = rec_b[(size_t)(c0 + 32 * i) * M + m];
                         }
 #pragma unroll
                         for (int i = 0; i < kRecLanes; ++i) {
@@ -358,9 +363,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
         }
         TR2(2);
         bound *= 1.0001f;  // rounding slack of the bound arithmetic (a violation below 2x is harmless: see imma_gemv.cuh)
+        // power-of-two scale: bound = f * 2^e with f in [0.5, 1) (exponent field; no frexp / ldexp calls on the chain)
         int e = 0;
-        if (bound > 0.f && bound < 3.0e38f) frexpf(bound, &e);
-        const float S = ldexpf(1.0f, 22 - e);
+        if (bound > 0.f && bound < 3.0e38f) e = min(max((int)((__float_as_uint(bound) >> 23) & 0xffu) - 126, -100), 100);
+        const float S = __uint_as_float((uint32_t)(127 + 22 - e) << 23);
         const float cS = rr * S;
         int qs = 0;
         unsigned char* dg = Bs + (size_t)m * A.units * 4 * kDigBlk;
@@ -412,8 +418,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
                         // round to nearest even through the 1.5 * 2^23 magic constant (|y| <= 2^22): no F2I
                         const int q = __float_as_int(y[b] + 12582912.f) - 0x4B400000;
                         qs += q;
-                        const int v = (j == 7) ? -q : (q << (7 - j));
-                        dw[b] = ((uint32_t)v + 0x00808080u) ^ 0x00808080u;
+                        dw[b] = ((uint32_t)(q * qmul) + 0x00808080u) ^ 0x00808080u;  // q << (7 - j), or -q for plane 7
                     }
                     const uint32_t t0 = __byte_perm(dw[0], dw[1], 0x5140), t1 = __byte_perm(dw[2], dw[3], 0x5140);
                     const uint32_t t2 = __byte_perm(dw[0], dw[1], 0x7362), t3 = __byte_perm(dw[2], dw[3], 0x7362);
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) q64 += __shfl_xor_sync(0xffffffffu, q64, o);
         if (lane == 0) atomicAdd(&s_qtot[m], (unsigned long long)q64);  // integer: order-independent
-        if (tid == 0) s_invd[m] = ldexp(1.0, e - 22);
+        if (tid == 0) s_invd[m] = (double)__uint_as_float((uint32_t)(127 + e - 22) << 23);
         TR2(4);
     }
     // residual rows of the consumer (resid records): in flight across the IMMA loop
@@ -444,12 +449,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
     imma::mbar_wait(&s_bar, 0);      // signs landed (issued long ago)
     TR2(5);
 
-    // ---- 3. IMMA loop: this warp's K units; B fragments in registers across all row tiles ----
-    int acc[TILES][4];
+    // ---- 3. IMMA loop: this warp's K units; B fragments in registers across all row tiles. Few row tiles per CTA (o_proj,
+    //         down_proj) mean few independent accumulator chains per warp: even / odd planes get their own there ----
+    constexpr int NACC = TILES <= 2 ? 2 : 1;
+    int accs[NACC][TILES][4];
 #pragma unroll
-    for (int r = 0; r < TILES; ++r)
+    for (int z = 0; z < NACC; ++z)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[r][i] = 0;
+        for (int r = 0; r < TILES; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) accs[z][r][i] = 0;
     for (int u = warp; u < A.units; u += kWarps) {
         uint4 bv[4];
 #pragma unroll
@@ -471,10 +480,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_k
                     const uint32_t mask = 0x01010101u << (2 * jp + jj);
                     const uint32_t a0 = imma::plane(w0.x, mask), a1 = imma::plane(w1.x, mask);
                     const uint32_t a2 = imma::plane(w0.y, mask), a3 = imma::plane(w1.y, mask);
-                    imma::imma16832(acc[r], a0, a1, a2, a3, jj ? bv[jp].z : bv[jp].x, jj ? bv[jp].w : bv[jp].y);
+                    imma::imma16832(accs[NACC == 2 ? jj : 0][r], a0, a1, a2, a3, jj ? bv[jp].z : bv[jp].x, jj ? bv[jp].w : bv[jp].y);
                 }
         }
     }
+    int acc[TILES][4];
+#pragma unroll
+    for (int r = 0; r < TILES; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[r][i] = NACC == 2 ? accs[0][r][i] + accs[NACC - 1][r][i] : accs[0][r][i];
 
     // ---- 4. combine the K split across warps (red aliases the weight region), finalise, store, records ----
     TR2(6);

@@ -152,6 +152,7 @@ def _wide(model, layers, tokens, batch, pdt, **env):
 
 
 @pytest.mark.parametrize("path,env", [("persistent", {"ONEBIT_PERSIST": "1"}), ("fused", {"ONEBIT_PERSIST": "0"}),
+                                      ("fused-v1", {"ONEBIT_PERSIST": "0", "ONEBIT_FUSED_V2": "0"}),
                                       ("split", {"ONEBIT_PERSIST": "0", "ONEBIT_FUSED": "0"})])
 @pytest.mark.parametrize("batch", [1, 4])
 def test_llama7b_width_logits_match_the_reference_port(path, env, batch):
@@ -161,12 +162,27 @@ def test_llama7b_width_logits_match_the_reference_port(path, env, batch):
     out = _wide("7b", 2, 5, batch, "f32", **env)
     assert out["status"] == 0
     assert out["persistent"] == (path == "persistent")
-    want = {"persistent": 1, "fused": 2 * 5 + 4, "split": 2 * 9 + 4}[path]
-    if path == "fused" and batch > 2:
+    want = {"persistent": 1, "fused": 2 * 5 + 4, "fused-v1": 2 * 5 + 4, "split": 2 * 9 + 4}[path]
+    if path.startswith("fused") and batch > 2:
         want = 2 * 9 + 4  # batches of 3..8 sequences run the split chain (glue kernel + GEMV) at these widths
     assert out["launches"] == want, out
     assert out["rel_l2"] < 2e-3, out
     assert out["argmax_agree"] == 1.0, out
+
+
+def test_fused_stage_with_two_sequences_at_llama7b_width():
+    """The second-generation fused stages (fused_gemv2.cuh) with two tokens per launch."""
+    out = _wide("7b", 2, 4, 2, "f16", ONEBIT_PERSIST="0")
+    assert out["status"] == 0 and out["launches"] == 2 * 5 + 4, out
+    assert out["rel_l2"] < 2e-3 and out["argmax_agree"] == 1.0, out
+
+
+def test_fused_stage_quantiser_bound_holds_under_outlier_channels():
+    """The fused stages size the 23-bit activation integers from a BOUND on max |x'| (records of the producer), not from
+    the vector itself: massive-activation channels (a few embedding columns x 60) must neither saturate nor cost parity."""
+    out = _wide("7b", 2, 5, 1, "f32", ONEBIT_PERSIST="0", ONEBIT_WIDE_OUTLIERS="1")
+    assert out["status"] == 0, out
+    assert out["rel_l2"] < 2e-3 and out["argmax_agree"] == 1.0, out
 
 
 @pytest.mark.parametrize("path,env", [("fused", {"ONEBIT_PERSIST": "0"})])

@@ -22,6 +22,9 @@ from oracle import oracle, ref_port  # noqa: E402
 def main(model, layers, tokens, batch, pdt):
     config = dict(LLAMA_7B if model == "7b" else LLAMA2_13B, num_hidden_layers=layers)
     sd = synthetic_state_dict(config, seed=3, param_dtype=torch.float32)
+    if os.environ.get("ONEBIT_WIDE_OUTLIERS") == "1":  # a few massive-activation channels in the residual stream
+        emb = sd["model.embed_tokens.weight"]
+        emb[:, [7, 1000, 2049]] *= 60.0
     ids = torch.randint(3, config["vocab_size"], (batch, tokens), generator=torch.Generator().manual_seed(5))
     with torch.no_grad():
         want, _ = ref_port.RefPortModel(config, sd).forward(ids)
