@@ -950,44 +950,28 @@ bool fused2_enabled() {
     return v == 1;
 }
 
-// 256 threads: two CTAs per SM (this stage's and the next one's), half of the shared memory each; 512 threads: one CTA per SM
-int fused2_threads() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("ONEBIT_FUSED2_THREADS");
-        v = (e && atoi(e) == 256) ? 256 : 512;
-    }
-    return v;
-}
-size_t fused2_smem_cap() { return fused2_threads() == 256 ? 110 * 1024 : 224 * 1024; }
-
 int fused2_rows_per_cta(int total_rows, int M, int K) {
-    const int sms = num_sms(), th = fused2_threads();
+    const int sms = num_sms();
     int rows = ((total_rows + sms - 1) / sms + 31) / 32 * 32;
     if (rows < 32) rows = 32;
     if (rows > 192) rows = 192;
     if (M > 2) return 0;
-    while (rows > 32 && fused2::smem_bytes(M, K, rows, th) > fused2_smem_cap()) rows -= 32;
-    if (fused2::smem_bytes(M, K, rows, th) > fused2_smem_cap()) return 0;
+    while (rows > 32 && fused2::smem_bytes(M, K, rows) > 224 * 1024) rows -= 32;
+    if (fused2::smem_bytes(M, K, rows) > 224 * 1024) return 0;
     return rows;
 }
 
-template <int TILES, int THREADS>
-int fused2_launch_inst2(const fused2::Args& a, int ctas, cudaStream_t s) {
-    auto kern = fused2::fused_gemv2_kernel<TILES, THREADS>;
+template <int TILES>
+int fused2_launch_inst(const fused2::Args& a, int ctas, cudaStream_t s) {
+    auto kern = fused2::fused_gemv2_kernel<TILES>;
     static bool configured[64] = {false};
     int dev = 0;
     ONEBIT_CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused2_smem_cap()));
-        ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ONEBIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         configured[dev] = true;
     }
-    return launch_pdl(kern, dim3(ctas), dim3(THREADS), fused2::smem_bytes(a.M, a.K, a.rows_per_cta, THREADS), s, a);
-}
-template <int TILES>
-int fused2_launch_inst(const fused2::Args& a, int ctas, cudaStream_t s) {
-    return fused2_threads() == 256 ? fused2_launch_inst2<TILES, 256>(a, ctas, s) : fused2_launch_inst2<TILES, 512>(a, ctas, s);
+    return launch_pdl(kern, dim3(ctas), dim3(fused2::kThreads), fused2::smem_bytes(a.M, a.K, a.rows_per_cta), s, a);
 }
 
 int fused2_launch(fused2::Args a, int ext_rep_stride, cudaStream_t s, int* ctas_per_problem) {
@@ -1000,20 +984,6 @@ int fused2_launch(fused2::Args a, int ext_rep_stride, cudaStream_t s, int* ctas_
         ctas += (a.p[i].n_rows + a.rows_per_cta - 1) / a.rows_per_cta;
     }
     *ctas_per_problem = (a.p[0].n_rows + a.rows_per_cta - 1) / a.rows_per_cta;
-    static int dup = -1;  // experiment: every stage twice (idempotent) — does the second launch find the code in the I-cache?
-    if (dup < 0) { const char* e = getenv("ONEBIT_DUP_STAGE"); dup = e ? atoi(e) : 0; }
-    if (dup > 0 && a.mode != fused::EMBED_NORM) {
-        fused2::Args b = a;
-        b.trace = 0;
-        int rc = ONEBIT_OK;
-        switch (a.rows_per_cta / 16) {
-            case 2: rc = fused2_launch_inst<2>(b, ctas, s); break;
-            case 6: rc = fused2_launch_inst<6>(b, ctas, s); break;
-            case 10: rc = fused2_launch_inst<10>(b, ctas, s); break;
-            default: break;
-        }
-        if (rc) return rc;
-    }
     switch (a.rows_per_cta / 16) {
         case 2: return fused2_launch_inst<2>(a, ctas, s);
         case 4: return fused2_launch_inst<4>(a, ctas, s);

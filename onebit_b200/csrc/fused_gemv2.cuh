@@ -1,28 +1,36 @@
-// Fused "glue + bit-plane IMMA GEMV" stage, second generation: the prologue has NO block-wide reduction.
+// Fused "glue + bit-plane IMMA GEMV" stage, second generation: nothing block-wide between the dependency wait and the
+// IMMA loop except ONE barrier, and nothing static left behind the wait.
 //
-// Round-1/2 measurements (profiles/r01_fused_gemv_ncu_full_summary.txt): two thirds of the 9.3 us a
-// fused stage costs are the glue prologue — three block reductions per token (LayerNorm sums, RMSNorm sum of squares,
-// max |x'| for the quantiser scale), each three __syncthreads deep, plus a shared-memory staging pass of x' because the
-// float4 loads and the quantiser disagree about which thread owns which column. The GEMV itself needs ~1.5 us.
-// This kernel removes every one of them from the dependency chain of the common stages:
-//   * the PRODUCER's epilogue emits, per CTA and token, everything its consumer needs as partial sums over the rows
-//     the CTA owns anyway: (sum t, sum t^2) as before, plus (sum r*t, sum r, sum r^2, max t, min t, max |r|) where r is
-//     the residual row the consumer will add. With mu / rstd from the first two,
+// What the in-kernel clocks of the first generation (fused_gemv.cuh) showed on B200 (tools/trace_gemv2.py,
+// profiles/r02_fused2_stage_trace.txt): of the ~16 k cycles of a stage, the IMMA loop is 1-4 k; the rest is a serial
+// program on the dependency chain — three block reductions per token (LayerNorm sums, RMSNorm sum of squares, max |x'|),
+// fp64 divisions and square roots in the statistics, frexp / ldexp calls, a shared-memory staging pass of x', launch
+// arguments fetched cold from the constant bank, static vectors fetched from DRAM after the wait, and a warp's bulk
+// copies serialised lane by lane by the compiler. This kernel removes them one by one:
+//   * the PRODUCER's epilogue emits, per CTA and token, everything its consumer needs as partial results over the rows
+//     the CTA owns anyway: base record (sum t, sum t^2, max t, min t) and resid record (sum r*t, sum r, sum r^2, max |r|),
+//     r = the residual row the consumer will add. With mu / rstd from the first two,
 //         sum (r + (t - mu) rstd)^2 = sum r^2 + 2 rstd (sum r t - mu sum r) + rstd^2 (sum t^2 - 2 mu sum t + N mu^2)
 //     is the RMSNorm denominator of modeling_bitllama.py:67-81 without touching the vector, and
 //         max |x'| <= (max |r| + max(|max t - mu|, |min t - mu|) rstd) * rms * max |ln_w * h|
-//     bounds the quantiser range (the 23-bit integers keep >= 19 bits under the bound; the scale stays a power of two).
-//     Every warp reduces the <= ~150 records with shuffles on its own: no barrier;
-//   * every thread loads exactly the four columns of the quantiser items it owns (columns 8b + j of one 32-bit weight
-//     word; a warp's four loads cover 128 consecutive floats), so x' never passes through shared memory;
+//     bounds the quantiser range: the scale stays a power of two >= the exact one, so the 23-bit integers lose a few
+//     low bits at most (tests: LLaMA-7B/13B widths, outlier channels) and can never saturate. The attention kernel
+//     emits max |out| per head for the o_proj stage. Every warp reduces the <= ~150 records with shuffles on its own
+//     (measured faster than one warp + broadcast), fp32 sums, fp64 only for the multiply-adds of E[t^2] - mu^2;
+//     every record array exists kReplicas times so that 128+ CTAs do not poll the same few L2 lines;
+//   * vectors between fused stages (t of o / gate / up / down, the residual stream) live in ITEM ORDER: the four
+//     columns 8b + j of one 32-bit weight word a quantiser item needs are adjacent, one 16-byte load per item, x' goes
+//     from registers to digits without a shared-memory pass (producers permute their 4-byte stores for free);
 //   * static factors (input_factor, RMSNorm weight * input_factor, weight_scale) come from fp32 side tables built at
-//     decoder creation in item order: one float4 per item, loaded before the programmatic-dependency wait;
-//   * sum_k q goes through one shared-memory integer atomic per warp, the epilogue needs one barrier for its records.
-// What is left between griddepcontrol.wait and the IMMA loop: one L2 round trip, ~100 ALU instructions, ONE barrier.
+//     decoder creation in item order; they are loaded (round 0) or prefetched into L2 (later rounds) BEFORE the wait;
+//   * the launch arguments are copied to shared memory once; all address arithmetic sits above the wait;
+//   * every warp issues its own share of the sign-slice bulk copies; sum_k q goes through one shared-memory integer
+//     atomic per warp; rounding uses the 1.5 * 2^23 constant instead of F2I; the epilogue needs one barrier for its
+//     records; the shared-memory pitch of the sign rows is conflict-free at every K (fused::row_pad).
+// Measured (profiles/r02_bench_default_line.json): LLaMA-7B batch 1 1.455 -> 1.207 ms/step, 9.33 -> 7.59 us per stage.
 //
-// Only the first stage of a step (token embedding, no producer) and the o_proj stage without attention records
-// (gemv_only timing mode) keep one block reduction. Reference semantics are those of fused_gemv.cuh
-// (bitnet.py:112-122 around modeling_bitllama.py:229-231,451-454,522-524,580,257).
+// Only the first stage of a step (token embedding, no producer) keeps one block reduction. Reference semantics are those
+// of fused_gemv.cuh (bitnet.py:112-122 around modeling_bitllama.py:229-231,451-454,522-524,580,257).
 #pragma once
 #include "fused_gemv.cuh"
 
@@ -94,9 +102,13 @@ __device__ __forceinline__ void finish_ln_fast(float s, float q, double inv_n, f
 
 using fused::row_pad;  // K = 11008 (1376 bytes per row) with a fixed 32-byte pad landed every row on the same banks
 
-inline size_t smem_bytes(int M, int K, int rows_per_cta, int threads) {
+constexpr int kThreads = 512;  // one CTA per SM (a 256-thread, two-CTAs-per-SM variant was measured: 1.69 vs 1.39 ms/step)
+constexpr int kWarps = kThreads / 32;
+constexpr int kItems = 1024 / kThreads;  // quantiser items per thread and glue round (a round = 1024 items per CTA)
+
+inline size_t smem_bytes(int M, int K, int rows_per_cta) {
     const size_t wbytes = (size_t)rows_per_cta * (K / 8 + row_pad(K / 8));
-    const size_t red = (size_t)(threads / 32) * rows_per_cta * 8 * 4;  // aliases the weight region after the main loop
+    const size_t red = (size_t)kWarps * rows_per_cta * 8 * 4;  // aliases the weight region after the main loop
     const size_t dig = (size_t)M * (K / 256) * 4 * kDigBlk;
     return (((wbytes > red ? wbytes : red) + 15) & ~(size_t)15) + dig + 64;
 }
@@ -120,12 +132,9 @@ __device__ __forceinline__ float wmin(float v) {
 // first column of item `it` (its four columns are c, c + 8, c + 16, c + 24)
 __host__ __device__ __forceinline__ int item_col(int it) { return ((it >> 3) << 5) + (it & 7); }
 
-// TILES = rows_per_cta / 16. THREADS = 512: one CTA per SM. THREADS = 256 (<= 128 registers, <= ~110 KB of shared
-// memory): TWO CTAs per SM, so that the CTAs of the next stage (programmatic dependent launch) sit on the same SMs with
-// their sign slices already in shared memory while this stage computes. A glue round = 1024 quantiser items per CTA.
-template <int TILES, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) fused_gemv2_kernel(const __grid_constant__ Args Ap) {
-    constexpr int kThreads = THREADS, kWarps = THREADS / 32, kItems = 1024 / THREADS;
+// TILES = rows_per_cta / 16 (compile-time: the accumulators of every row tile live in registers across K).
+template <int TILES>
+__global__ void __launch_bounds__(kThreads, 1) fused_gemv2_kernel(const __grid_constant__ Args Ap) {
     extern __shared__ __align__(16) unsigned char smem[];
     // The launch parameters live in the constant bank, cold at every launch: scattered first touches cost an L2 round trip
     // each, in program order, on the dependency chain. One cooperative copy into shared memory up front instead.
