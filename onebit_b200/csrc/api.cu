@@ -57,9 +57,11 @@ static int check_forward_args(const void* x, const int8_t* w, const void* g, con
 static int pick_variant(int variant, int64_t m, int64_t k, int64_t n, int act_dtype, int* chosen) {
     switch (variant) {
         case ONEBIT_VARIANT_AUTO:  // decode-size batches: bit-plane IMMA GEMV; larger: tcgen05; odd shapes: CUDA cores
+            // (small batches at widths whose digits do not fit the GEMV's shared memory — e.g. 5..8 tokens at K = 11008 —
+            //  go to the tcgen05 tile as well: the CUDA-core kernel is a 2-3 %-of-HBM anchor, not a fallback to land on)
             *chosen = matvec_mma_supported(m, k, n, act_dtype)
                           ? ONEBIT_VARIANT_MMA
-                          : (m > 8 && prefill_tc5_supported(m, k, n) ? ONEBIT_VARIANT_TC5 : ONEBIT_VARIANT_SIMT);
+                          : (m > 4 && prefill_tc5_supported(m, k, n) ? ONEBIT_VARIANT_TC5 : ONEBIT_VARIANT_SIMT);
             return ONEBIT_OK;
         case ONEBIT_VARIANT_SIMT:
             *chosen = variant;

@@ -444,7 +444,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_gemv2_kernel(const __grid_c
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) q64 += __shfl_xor_sync(0xffffffffu, q64, o);
         if (lane == 0) atomicAdd(&s_qtot[m], (unsigned long long)q64);  // integer: order-independent
-        if (tid == 0) s_invd[m] = (double)__uint_as_float((uint32_t)(127 + e - 22) << 23);
+        // a non-finite bound (NaN / Inf anywhere upstream reaches it through the records) poisons the outputs of this token,
+        // as the reference's fp arithmetic would, instead of being quantised into finite garbage
+        if (tid == 0) s_invd[m] = bound == bound && bound < 3.0e38f ? (double)__uint_as_float((uint32_t)(127 + e - 22) << 23) : (double)NAN;
         TR2(4);
     }
     // residual rows of the consumer (resid records): in flight across the IMMA loop

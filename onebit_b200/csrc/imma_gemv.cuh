@@ -344,7 +344,7 @@ __device__ __forceinline__ void quantize_from_smem(const float* xs, int K, float
         long long tot = 0;
         for (int w = 0; w < nw; ++w) tot += ls[w];
         QMeta qm;
-        qm.inv_scale = ldexp(1.0, e - 22);
+        qm.inv_scale = am < 3.0e38f ? ldexp(1.0, e - 22) : (double)NAN;  // Inf input: the token's outputs are NaN, not finite garbage
         qm.qtot = tot;
         *qmeta = qm;
     }

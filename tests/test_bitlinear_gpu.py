@@ -438,3 +438,29 @@ def test_tcgen05_bfloat16_activations_keep_their_range():
     # fp16 parameters next to bf16 activations: input_factor is re-rounded to bf16 (documented), result stays finite and close
     y = run(dict(c2, bias=None), "bf16", "tc5", param="f16")
     assert np.isfinite(y).all()
+
+
+def test_auto_dispatch_for_small_batches_at_wide_k_matches_the_oracle():
+    """AUTO must not land on the CUDA-core anchor for 5..8 tokens at widths whose digits do not fit the IMMA GEMV's shared
+    memory (K = 11008: down_proj): those go to the tcgen05 tile. Checked through the public forward."""
+    for m in (5, 8):
+        k, n = 11008, 4096
+        assert "mma" not in variants_for(m, k, n)  # the reason the case exists
+        case = oracle.synth_case(4200 + m, k, n, m)
+        want = oracle.bitlinear_forward_c(case["x"], case["packed"], case["g"], case["h"])
+        got_auto, got_tc5 = run(case, "f16", "auto"), run(case, "f16", "tc5")
+        assert oracle.rel_l2(got_auto, want) < REL_TOL
+        assert np.array_equal(got_auto, got_tc5)  # AUTO picked the tcgen05 variant
+
+
+def test_infinite_input_poisons_the_token_instead_of_finite_garbage():
+    """An Inf in a token's input makes that token's outputs non-finite (the reference's fp arithmetic propagates it);
+    the other token of the batch is untouched (decode GEMV quantiser)."""
+    k, n, m = 4096, 4096, 2
+    case = oracle.synth_case(77, k, n, m)
+    want = oracle.bitlinear_forward_c(case["x"], case["packed"], case["g"], case["h"])
+    t = to_dev(case, torch.float16)
+    t["x"][1, 5] = float("inf")
+    y = onebit_b200.bitlinear_forward(t["x"], t["w"], t["g"], t["h"], t["b"], variant="mma").float().cpu().numpy()
+    assert not np.isfinite(y[1]).any()
+    assert oracle.rel_l2(y[0], want[0]) < REL_TOL
