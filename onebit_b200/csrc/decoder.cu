@@ -47,6 +47,9 @@ struct GlueArgs {
     int mode, M, K, nprob, write_x_f16;
     int stats_from_data;  // RESID_NORM / SILU_MUL: (sum, sumsq) of t_a (t_b) from the data itself (all-reduced inputs; prompt pass)
     int n_ln;             // LayerNorm denominator of the producer(s) when it is not K (tensor-parallel shards); 0 = K
+    // batched decode, single GPU: t_a (t_b) still are `ksplit` split-K partial slabs `slab` floats apart — summed while
+    // loading (fixed order), statistics from the data: no separate reduce + statistics launch between GEMM and glue
+    int ksplit; long long slab;
     const float* t_a; const float* stats_a; int ncta_a;   // previous GEMV output (already * g), [ncta][M][2] partials
     const float* t_b; const float* stats_b; int ncta_b;
     const float* resid_in; float* resid_out;              // [M][K] fp32
@@ -159,6 +162,33 @@ __global__ void __launch_bounds__(kGlueThreads, 1) glue_kernel(const __grid_cons
             if (b4) vb[i] = b4[i4];
             if (norm_mode) vw[i] = fused::ldraw4<TP>(static_cast<const TP*>(A.ln_w), i4);
             if (need_h) vh[i] = fused::ldraw4<TP>(static_cast<const TP*>(A.h[p]), i4);
+        }
+    }
+    // ---- split-K partial slabs of the producer GEMM (batched decode, single GPU): summed in slab order, ZG slabs of loads
+    //      in flight at a time
+    if (A.ksplit > 1 && (A.mode == GLUE_RESID_NORM || A.mode == GLUE_SILU_MUL)) {
+        constexpr int ZG = NV4 <= 2 ? 4 : (NV4 <= 3 ? 2 : 1);
+        const long long slab4 = A.slab >> 2;
+        for (int z0 = 1; z0 < A.ksplit; z0 += ZG) {
+            float4 wa[ZG][NV4], wb[ZG][NV4];
+#pragma unroll
+            for (int zz = 0; zz < ZG; ++zz)
+#pragma unroll
+                for (int i = 0; i < NV4; ++i) {
+                    const int i4 = i * kGlueThreads + tid;
+                    wa[zz][i] = zero4; wb[zz][i] = zero4;
+                    if (i4 < K4 && z0 + zz < A.ksplit) {
+                        wa[zz][i] = a4[(z0 + zz) * slab4 + i4];
+                        if (A.mode == GLUE_SILU_MUL) wb[zz][i] = b4[(z0 + zz) * slab4 + i4];
+                    }
+                }
+#pragma unroll
+            for (int zz = 0; zz < ZG; ++zz)
+#pragma unroll
+                for (int i = 0; i < NV4; ++i) {
+                    va[i].x += wa[zz][i].x; va[i].y += wa[zz][i].y; va[i].z += wa[zz][i].z; va[i].w += wa[zz][i].w;
+                    vb[i].x += wb[zz][i].x; vb[i].y += wb[zz][i].y; vb[i].z += wb[zz][i].z; vb[i].w += wb[zz][i].w;
+                }
         }
     }
     // ---- LayerNorm statistics of the producer(s) (bitnet.py:118), from the GEMV's per-CTA partials
@@ -679,6 +709,7 @@ struct onebit_decoder {
     __half* h16_store = nullptr;
     __half* xI_f16 = nullptr;        // [B][I]
     float *red_o = nullptr, *red_d = nullptr;  // [max_batch][2]
+    int tc5_ks_d = 1;  // split-K factor of the last down_proj launch (single GPU: its partials are summed by the consuming glue)
     // split-KV decode attention: slices per (sequence, head) (fixed by max_seq_len so that a captured graph stays valid),
     // partial records, merge tickets
     int attn_nsplit = 1;
@@ -1144,8 +1175,9 @@ int tc5_ksplit(int row_tiles, int K, int ksplit_max) {
 // Batched decode (5..64 sequences per replica): every BitLinear runs on the tcgen05 path (prefill_tc5.cu, decode tile
 // configuration: weights as the 128-row UMMA M operand with input_factor folded in, the M tokens as UMMA N, split-K over
 // grid.z), the glue kernels hand it fp16 activations, a reduce pass sums the K splits and emits the LayerNorm statistics.
-// Per layer: glue | q,k,v (one launch) | reduce | attention | glue | o | reduce | glue | gate,up (one launch) | reduce |
-// glue | down | reduce = 13 launches.
+// Per layer: glue | q,k,v (one launch) | reduce | attention | glue | o | glue | gate,up (one launch) | glue | down = 10
+// launches on a single GPU (the glue after o / gate,up / down sums the split-K partials itself and takes the LayerNorm
+// statistics from the data); tensor-parallel shards keep a reduce pass before each all-reduce: 13 launches.
 int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int* cur_io, bool only_proj = false) {
     const onebit_decoder_config& C = D->cfg;
     const int H = C.hidden_size, I = C.intermediate_size, pd = C.param_dtype, B = C.max_batch;
@@ -1167,7 +1199,8 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         GlueArgs g = {};
         g.mode = l == 0 ? GLUE_EMBED_NORM : GLUE_RESID_NORM;
         g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
-        g.t_a = D->t_d; g.stats_a = D->red_d; g.ncta_a = kReduceSlices; g.stats_from_data = tp > 1;
+        g.t_a = D->t_d; g.stats_a = D->red_d; g.ncta_a = kReduceSlices; g.stats_from_data = 1;
+        if (tp == 1 && l > 0) { g.ksplit = D->tc5_ks_d; g.slab = (long long)M * H; }
         g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1];
         g.embed = D->embed; g.ids = D->ids; g.ln_w = P.input_layernorm; g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
         if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
@@ -1211,12 +1244,16 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         t.x16 = D->x_f16; t.M = M; t.K = Hk; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, Hk, D->ksplit_max);
         t.p[0].w = static_cast<const int8_t*>(P.o.weight); t.p[0].h16 = h16[3]; t.p[0].g = P.o.weight_scale; t.p[0].t = D->t_o; t.p[0].N = H;
         rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
-        rc = reduce(D->t_o, nullptr, nullptr, H, 1, t.ksplit, D->red_o); if (rc) return rc;
-        if (!only_proj) { rc = allreduce(D, D->t_o, (int64_t)M * H, s); if (rc) return rc; }
+        const int ks_o = t.ksplit;
+        if (tp > 1) {  // (single GPU: the consuming glue sums the split-K partials and takes the statistics from the data)
+            rc = reduce(D->t_o, nullptr, nullptr, H, 1, t.ksplit, D->red_o); if (rc) return rc;
+            if (!only_proj) { rc = allreduce(D, D->t_o, (int64_t)M * H, s); if (rc) return rc; }
+        }
         // ---- glue 3: resid + LN(o) -> RMSNorm -> fp16 x (statistics from the all-reduced data under tensor parallelism)
         g = {};
         g.mode = GLUE_RESID_NORM; g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
-        g.t_a = D->t_o; g.stats_a = D->red_o; g.ncta_a = kReduceSlices; g.stats_from_data = tp > 1;
+        g.t_a = D->t_o; g.stats_a = D->red_o; g.ncta_a = kReduceSlices; g.stats_from_data = 1;
+        if (tp == 1) { g.ksplit = ks_o; g.slab = (long long)M * H; }
         g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = P.post_attention_layernorm;
         g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps;
         if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
@@ -1233,13 +1270,17 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
             t.p[i].t = tg[i]; t.p[i].N = Il; t.p[i].ldt = Ik;
         }
         rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
-        rc = reduce(tg[0], tg[1], nullptr, Ik, 2, t.ksplit, D->red_gu); if (rc) return rc;
-        if (!only_proj) { rc = allreduce(D, D->red_gu, (int64_t)2 * kReduceSlices * M * 2, s); if (rc) return rc; }
+        const int ks_gu = t.ksplit;
+        if (tp > 1) {
+            rc = reduce(tg[0], tg[1], nullptr, Ik, 2, t.ksplit, D->red_gu); if (rc) return rc;
+            if (!only_proj) { rc = allreduce(D, D->red_gu, (int64_t)2 * kReduceSlices * M * 2, s); if (rc) return rc; }
+        }
         // ---- glue 4: silu(LN(gate)) * LN(up) -> fp16 [M][Ik]
         g = {};
         g.mode = GLUE_SILU_MUL; g.M = M; g.K = Ik; g.nprob = 1; g.write_x_f16 = 1; g.x_f16 = D->xI_f16; g.n_ln = I;
         g.t_a = tg[0]; g.stats_a = D->red_gu; g.ncta_a = kReduceSlices;
         g.t_b = tg[1]; g.stats_b = D->red_gu + (size_t)kReduceSlices * M * 2; g.ncta_b = kReduceSlices;
+        if (tp == 1) { g.ksplit = ks_gu; g.slab = (long long)M * Ik; g.stats_from_data = 1; }
         g.ln_eps = C.ln_eps;
         if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
         // ---- down_proj (row-parallel) + all-reduce of the partial sums
@@ -1247,8 +1288,11 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         t.x16 = D->xI_f16; t.M = M; t.K = Ik; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, Ik, D->ksplit_max);
         t.p[0].w = static_cast<const int8_t*>(P.down.weight); t.p[0].h16 = h16[6]; t.p[0].g = P.down.weight_scale; t.p[0].t = D->t_d; t.p[0].N = H;
         rc = launch_tc5(t, s); if (rc) return rc; ++*launches;
-        rc = reduce(D->t_d, nullptr, nullptr, H, 1, t.ksplit, D->red_d); if (rc) return rc;
-        if (!only_proj) { rc = allreduce(D, D->t_d, (int64_t)M * H, s); if (rc) return rc; }
+        D->tc5_ks_d = t.ksplit;
+        if (tp > 1) {
+            rc = reduce(D->t_d, nullptr, nullptr, H, 1, t.ksplit, D->red_d); if (rc) return rc;
+            if (!only_proj) { rc = allreduce(D, D->t_d, (int64_t)M * H, s); if (rc) return rc; }
+        }
     }
     *cur_io = cur;
     return ONEBIT_OK;
@@ -1578,6 +1622,7 @@ static int decoder_step_impl(onebit_decoder* D, int batch, const int64_t* forced
     g.mode = GLUE_RESID_NORM; g.M = M; g.K = H; g.nprob = 1; g.write_x_f16 = 1;
     g.t_a = D->t_d; g.stats_a = use_tc5 ? D->red_d : D->st_d; g.ncta_a = use_tc5 ? kReduceSlices : (use_fused ? nc_d : cH);
     g.stats_from_data = D->tp > 1;
+    if (use_tc5 && D->tp == 1) { g.stats_from_data = 1; g.ksplit = D->tc5_ks_d; g.slab = (long long)M * H; }
     g.resid_in = D->resid[cur]; g.resid_out = D->resid[cur ^ 1]; g.ln_w = D->final_norm;
     g.ln_eps = C.ln_eps; g.rms_eps = C.rms_eps; g.x_f16 = D->x_f16;
     rc = glue_launch(D, g, s); if (rc) return rc; ++launches;
