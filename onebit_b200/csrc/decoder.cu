@@ -313,6 +313,7 @@ struct AttnArgs {
     float* part;                    // [M][n_heads][nsplit][kHeadDim + 2]
     int* tickets;                   // [M][n_heads], zero between launches
     float* amax;                    // [M][n_heads] max |out| of every (sequence, head): quantiser bound of the o_proj stage, or nullptr
+    __half* out16;                  // optional fp16 copy of `out` with row stride out_ld (the batched path's o_proj reads it through TMA)
 };
 
 __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ AttnArgs A) {
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     if (nsplit == 1) {
         const float o = acc * inv;
         A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = o;
+        if (A.out16 != nullptr) A.out16[(size_t)m * A.out_ld + hd * kHeadDim + d] = __float2half_rn(o);
         if (A.amax != nullptr) {
             const float wm = fused2::wmax(fabsf(o));
             if (lane == 0) red[warp] = wm;  // (last read of red was before two barriers)
@@ -505,6 +507,7 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
     }
     const float o = num / den;
     A.out[(size_t)m * A.out_ld + hd * kHeadDim + d] = o;
+    if (A.out16 != nullptr) A.out16[(size_t)m * A.out_ld + hd * kHeadDim + d] = __float2half_rn(o);
     if (A.amax != nullptr) {
         const float wm = fused2::wmax(fabsf(o));
         if (lane == 0) red[warp] = wm;
@@ -1175,9 +1178,10 @@ int tc5_ksplit(int row_tiles, int K, int ksplit_max) {
 // Batched decode (5..64 sequences per replica): every BitLinear runs on the tcgen05 path (prefill_tc5.cu, decode tile
 // configuration: weights as the 128-row UMMA M operand with input_factor folded in, the M tokens as UMMA N, split-K over
 // grid.z), the glue kernels hand it fp16 activations, a reduce pass sums the K splits and emits the LayerNorm statistics.
-// Per layer: glue | q,k,v (one launch) | reduce | attention | glue | o | glue | gate,up (one launch) | glue | down = 10
-// launches on a single GPU (the glue after o / gate,up / down sums the split-K partials itself and takes the LayerNorm
-// statistics from the data); tensor-parallel shards keep a reduce pass before each all-reduce: 13 launches.
+// Per layer: glue | q,k,v (one launch) | reduce | attention | o | glue | gate,up (one launch) | glue | down = 9 launches on a
+// single GPU (the glue after o / gate,up / down sums the split-K partials itself and takes the LayerNorm statistics from
+// the data; the attention kernel writes o_proj's fp16 activations); tensor-parallel shards keep a reduce pass before each
+// all-reduce and a glue that zero-pads the attention output: 13 launches.
 int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int* cur_io, bool only_proj = false) {
     const onebit_decoder_config& C = D->cfg;
     const int H = C.hidden_size, I = C.intermediate_size, pd = C.param_dtype, B = C.max_batch;
@@ -1230,6 +1234,9 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         at.kcache = D->kcache + l * layer_cache; at.vcache = D->vcache + l * layer_cache;
         // many (sequence, head) CTAs: stream the cached rows from L2 instead of staging them (several CTAs per SM)
         at.out = D->attn_out; at.ln_eps = C.ln_eps;
+        // no padding columns (single GPU): the attention kernel writes the fp16 activations of o_proj itself
+        const bool attn_writes_x16 = Hk == Hl;
+        if (attn_writes_x16) at.out16 = D->x_f16;
         const size_t asmem = attn_finish_args(D, at, M, true);
         if (!only_proj) {
             rc = launch_attn( dim3(M, D->heads_l, at.nsplit), dim3(kHeadDim), asmem, s, at);
@@ -1238,7 +1245,7 @@ int run_tc5_layers(onebit_decoder* D, int M, cudaStream_t s, int* launches, int*
         // ---- glue 2: attention output [M][Hk] (pad columns stay zero) -> fp16
         g = {};
         g.mode = GLUE_PLAIN; g.M = M; g.K = Hk; g.nprob = 1; g.x_plain = D->attn_out; g.write_x_f16 = 1; g.x_f16 = D->x_f16;
-        if (!only_proj) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
+        if (!only_proj && !attn_writes_x16) { rc = glue_launch(D, g, s); if (rc) return rc; ++*launches; }
         // ---- o_proj (row-parallel: K slice) + all-reduce of the partial sums
         t = {};
         t.x16 = D->x_f16; t.M = M; t.K = Hk; t.nprob = 1; t.param_dtype = pd; t.ksplit = tc5_ksplit((H + 127) / 128, Hk, D->ksplit_max);
