@@ -216,8 +216,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dec.step()
         e1.record()
         barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        out = {"batch": B, "value": nrep * B * K / (ms * 1e-3), "ms_per_step": ms / K, "launches_per_step": dec.launches_per_step(),
+        if tp:  # one replica spread over the ranks: its tokens count once, over the slowest rank's time
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            value = B * K / (ms * 1e-3)
+        else:   # independent replicas: all tokens of all ranks over the slowest rank's time
+            agg = replicas.aggregate_throughput(B * K, e0.elapsed_time(e1), device=dev)
+            ms, value = agg["ms"], agg["per_s"]
+        out = {"batch": B, "value": value, "ms_per_step": ms / K, "launches_per_step": dec.launches_per_step(),
                "prompt_len": prompt_len, "tp_allreduce": getattr(dec, "tp_allreduce", "none")}
         # ---- end to end through the public API: ids from pinned host memory in, next ids back to the host, every step
         if with_e2e:

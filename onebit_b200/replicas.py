@@ -28,14 +28,3 @@ def aggregate_throughput(local_units: float, local_ms: float, device="cpu", grou
     total = sum_over_ranks(local_units, device, group)
     ms = max_over_ranks(local_ms, device, group)
     return {"units": total, "ms": ms, "per_s": total / (ms * 1e-3)}
-
-
-def shard_rows(n_rows: int, world: int, rank: int, multiple: int = 32) -> tuple[int, int]:
-    """Row range [begin, end) of a column-parallel (N-sharded) BitLinear for `rank`, in multiples of the GEMV's
-    32-row CTA tile; the last rank takes the remainder."""
-    per = (n_rows // world) // multiple * multiple
-    if per == 0:
-        raise ValueError(f"cannot shard {n_rows} rows over {world} ranks in multiples of {multiple}")
-    begin = rank * per
-    end = n_rows if rank == world - 1 else begin + per
-    return begin, end

@@ -43,13 +43,3 @@ def test_replica_aggregation_world2():
 def test_single_process_is_identity():
     assert replicas.max_over_ranks(1.5) == 1.5
     assert replicas.aggregate_throughput(10, 2.0)["per_s"] == 5000.0
-
-
-def test_shard_rows_cover_everything_in_tiles_of_32():
-    for n, world in [(4096, 2), (4096, 8), (11008, 4), (13824, 8), (5120, 8)]:
-        spans = [replicas.shard_rows(n, world, r) for r in range(world)]
-        assert spans[0][0] == 0 and spans[-1][1] == n
-        for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
-            assert e0 == b1 and b0 % 32 == 0
-    with pytest.raises(ValueError):
-        replicas.shard_rows(64, 8, 0)
