@@ -346,6 +346,12 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
             imma::bulk_g2s(Vs, vc, (uint32_t)(pos * kHeadDim * 2), &kv_bar);
         }
     }
+    // raw q / k / v of this thread's dimension and its rotate_half partner, RoPE factors: in flight while the LayerNorm sums
+    // are reduced (one exposed L2 round trip instead of two)
+    const size_t col = (size_t)m * A.H + hd * kHeadDim;
+    const int half = kHeadDim / 2, dp = d < half ? d + half : d - half, fi = d < half ? d : d - half;
+    const float c = A.rope_cos[(size_t)pos * half + fi], s = A.rope_sin[(size_t)pos * half + fi];
+    const float tq0 = A.t_q[col + d], tq1 = A.t_q[col + dp], tk0 = A.t_k[col + d], tk1 = A.t_k[col + dp], tv0 = A.t_v[col + d];
     float mq, rq, mk, rk, mv, rv;
     {
         // every warp sums the per-CTA partials on its own (lane c takes CTAs c, c + 32, ...; all loads of a round of 160
@@ -381,15 +387,12 @@ __global__ void __launch_bounds__(kHeadDim) attn_kernel(const __grid_constant__ 
             *ro[j] = rsqrtf(fmaxf((float)var, 0.f) + A.ln_eps);
         }
     }
-    const size_t col = (size_t)m * A.H + hd * kHeadDim;
-    const int half = kHeadDim / 2, dp = d < half ? d + half : d - half, fi = d < half ? d : d - half;
-    const float c = A.rope_cos[(size_t)pos * half + fi], s = A.rope_sin[(size_t)pos * half + fi];
-    const float q0 = (A.t_q[col + d] - mq) * rq, q1 = (A.t_q[col + dp] - mq) * rq;
-    const float k0 = (A.t_k[col + d] - mk) * rk, k1 = (A.t_k[col + dp] - mk) * rk;
+    const float q0 = (tq0 - mq) * rq, q1 = (tq1 - mq) * rq;
+    const float k0 = (tk0 - mk) * rk, k1 = (tk1 - mk) * rk;
     // rotate_half: (-x2, x1)  (modeling_bitllama.py:168-181)
     const float qr = d < half ? q0 * c - q1 * s : q0 * c + q1 * s;
     const float kr = d < half ? k0 * c - k1 * s : k0 * c + k1 * s;
-    const float vv = (A.t_v[col + d] - mv) * rv;
+    const float vv = (tv0 - mv) * rv;
     if (owns_new) {
         kc[(size_t)pos * kHeadDim + d] = __float2half_rn(kr);
         vc[(size_t)pos * kHeadDim + d] = __float2half_rn(vv);
