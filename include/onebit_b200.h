@@ -124,10 +124,11 @@ ONEBIT_API void onebit_layer_destroy(onebit_layer* layer);
  * sequences with a static KV cache: embedding (:1202), per layer RMSNorm (:67-81) -> q/k/v BitLinearInf
  * (:522-524) -> RoPE (:176-181) -> attention over the cache (:543-563) -> o_proj (:580) -> residual ->
  * RMSNorm -> gate/up BitLinearInf -> SiLU*up -> down_proj (:257) -> residual; final RMSNorm (:1315), lm_head
- * (:1610) and greedy argmax (generation/utils.py:2540). Every BitLinear runs through the bit-plane IMMA GEMV;
- * the glue between them (LayerNorm of bitnet.py:118, residual adds, norms, activation quantisation) is fused
- * into small kernels, so one step is ~9 launches per layer and is CUDA-graph capturable (position and token ids
- * live in device memory and are advanced on the device).
+ * (:1610) and greedy argmax (generation/utils.py:2540). Batches of 1..4 sequences run every BitLinear through the
+ * bit-plane IMMA GEMV, 5..64 through the tcgen05 decode tile; the glue between them (LayerNorm of bitnet.py:118,
+ * residual adds, norms, activation quantisation) is fused into the GEMV stages (5 launches per layer at batch 1..2)
+ * or into small kernels (9 per layer otherwise); a step is CUDA-graph capturable (position and token ids live in
+ * device memory and are advanced on the device).
  * All pointers in the parameter structs are DEVICE pointers that must outlive the decoder. Floating-point
  * parameters (weight_scale, input_factor, norm weights) are `param_dtype`; embed_tokens / lm_head are fp16. */
 typedef struct onebit_bitlinear_params {

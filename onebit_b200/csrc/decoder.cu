@@ -7,8 +7,12 @@
 // Every BitLinearInf (bitnet.py:112-122) = IMMA GEMV (imma_gemv.cuh) + the LayerNorm of bitnet.py:118, whose
 // statistics come from per-CTA partial sums the GEMV emits and are applied in the consumer's prologue.
 //
-// Kernels per layer (9): glue(resid+norm -> q/k/v digits) | GEMV qkv | attention | glue(o digits) | GEMV o |
-// glue(resid+norm -> gate/up digits) | GEMV gate,up | glue(silu*up -> down digits) | GEMV down.
+// Launches per layer, by path:
+//   batch 1..2, one GPU   5: fused stage q,k,v | attention | fused o | fused gate,up | fused down   (fused_gemv2.cuh)
+//   batch 1..2, tp > 1    5 + 2 statistics reductions + 4 small all-reduces                          (fused_gemv.cuh)
+//   batch 3..4            9: glue | GEMV qkv | attention | glue | GEMV o | glue | GEMV gate,up | glue | GEMV down
+//   batch 5..64           9 (one GPU) / 13 (tp > 1) on the tcgen05 decode tile, see run_tc5_layers
+//   ONEBIT_PERSIST=1      the whole step is one cooperative kernel (persist_step.cu)
 // All state that changes between steps (token ids, positions) lives in device memory, so a step is one
 // CUDA graph replay. The residual stream is kept in fp32.
 #include <algorithm>
