@@ -35,6 +35,20 @@ def model_config(name: str):
     return {"7b": ("LLaMA-7B-OneBit", LLAMA_7B), "13b": ("LLaMA2-13B-OneBit", LLAMA2_13B)}[name]
 
 
+def workload_config(name: str, B: int, world: int, tp: bool, tp_allreduce=None, prompt_len: int = 16) -> dict:
+    """The `config` object of the JSON line — the same for both arms (the reference arm runs this workload's op sequence
+    on the host cores; what it samples is said in its `cpu_baseline.sample` / `note`)."""
+    return {"workload": f"{name} greedy decode, batch {B} per GPU, {prompt_len}-token prompt then greedy decode steps, "
+                        f"static KV cache, one CUDA-graph replay per step",
+            "replicas": 1 if (tp and world > 1) else world,
+            "parallelism": (f"tp{world}: one tensor-parallel replica, 4 all-reduces per layer ({tp_allreduce}: "
+                            "one-shot Lamport all-reduce over NVLink peer memory, csrc/p2p_allreduce.cu)"
+                            if (tp and world > 1) else f"{world} independent replica(s), no data-path collective"),
+            "l2": "per-step weight stream 1.07 GB > 126 MB L2 (no flush needed)",
+            "activation_dtype": ("fp32 residual / fp16 KV cache / 23-bit integer BitLinear inputs" if B <= 4 else
+                                 "fp32 residual / fp16 KV cache / fp16 BitLinear inputs (tcgen05 kind::f16, fp32 accumulate)")}
+
+
 def bitlinear_bytes(cfg, batch: int) -> dict:
     """Algorithmic bytes: packed signs + fp16 x/y + fp16 g/h per BitLinear call."""
     H, I, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_hidden_layers"]
@@ -143,7 +157,9 @@ def run_reference(args, rank: int):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
             "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{name} greedy decode, batch {args.batch}, reference CPU path (torch ATen ops)"},
+            "config": workload_config(name, args.batch, max(1, args.gpus), False),
+            "note": "reference CPU path: the reference's op sequence for this workload (torch ATen ops, fp32) timed on the host "
+                    "cores over one decoder layer + lm_head and EXTRAPOLATED to the model's layer count (cpu_baseline.sample)",
             "cpu_baseline": res, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -343,15 +359,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if (args.tp and world > 1) else "weak", "vs_baseline": None,
             "dtype": "int8" if B <= 4 else "f16", "data": "synthetic",
-            "config": {"workload": f"{name} greedy decode, batch {B} per GPU, {main_res['prompt_len']}-token prompt then {K} "
-                                   f"generated tokens, static KV cache, one CUDA-graph replay per step",
-                       "replicas": 1 if (args.tp and world > 1) else world,
-                       "parallelism": (f"tp{world}: one tensor-parallel replica, 4 all-reduces per layer ({main_res.get('tp_allreduce')}: "
-                                       "one-shot Lamport all-reduce over NVLink peer memory, csrc/p2p_allreduce.cu)"
-                                       if (args.tp and world > 1) else f"{world} independent replica(s), no data-path collective"),
-                       "l2": "per-step weight stream 1.07 GB > 126 MB L2 (no flush needed)",
-                       "activation_dtype": ("fp32 residual / fp16 KV cache / 23-bit integer BitLinear inputs" if B <= 4 else
-                                            "fp32 residual / fp16 KV cache / fp16 BitLinear inputs (tcgen05 kind::f16, fp32 accumulate)")},
+            "config": workload_config(name, B, world, bool(args.tp), main_res.get("tp_allreduce"), main_res["prompt_len"]),
             "e2e": main_res["e2e"],
             "gpu_launches": main_res["launches_per_step"] * K, "launches_per_step": main_res["launches_per_step"],
             "roofline": main_res.get("roofline"), "clocks": clocks}
