@@ -170,7 +170,6 @@ class BitLinearB200(nn.Module):
         self.in_features = in_features
         self.out_features = out_features
         self.groups = groups  # unused, as in the reference (bitnet.py:77)
-        self.eps = 1e-5       # nn.LayerNorm default used at bitnet.py:86
         self.variant = "auto"
         self.weight = nn.Parameter(torch.empty((out_features, in_features // 8), device=device, dtype=torch.int8),
                                    requires_grad=False)
@@ -180,6 +179,9 @@ class BitLinearB200(nn.Module):
             self.bias = nn.Parameter(torch.empty(out_features, **factory_kwargs), requires_grad=False)
         else:
             self.register_parameter("bias", None)
+        # bitnet.py:86 — kept as an attribute like the reference's (no parameters, no state-dict keys); the fused kernels
+        # read its eps, they never call it
+        self.layernorm = nn.LayerNorm(out_features, elementwise_affine=False)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -203,7 +205,7 @@ class BitLinearB200(nn.Module):
         new.out_features = ref.out_features
         new.groups = getattr(ref, "groups", 1)
         ln = getattr(ref, "layernorm", None)
-        new.eps = float(getattr(ln, "eps", 1e-5))
+        new.layernorm = ln if isinstance(ln, nn.LayerNorm) else nn.LayerNorm(ref.out_features, elementwise_affine=False)
         new.variant = "auto"
         new.weight = ref.weight
         new.weight_scale = ref.weight_scale
@@ -214,6 +216,10 @@ class BitLinearB200(nn.Module):
             new.register_parameter("bias", None)
         new.train(ref.training)
         return new
+
+    @property
+    def eps(self) -> float:
+        return float(self.layernorm.eps)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         return bitlinear_forward(input, self.weight, self.weight_scale, self.input_factor, self.bias, self.eps,

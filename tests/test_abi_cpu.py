@@ -57,6 +57,10 @@ def test_module_surface_matches_reference_bitlinearinf():
     assert h.weight.dtype == torch.int8 and h.weight_scale.dtype == torch.float16  # int8 survives .half()
     with pytest.raises(ValueError):
         BitLinearB200(60, 8)
+    # bitnet.py:86: the reference keeps an affine-free nn.LayerNorm attribute; so does the mirror (no parameters, no keys)
+    assert isinstance(m.layernorm, torch.nn.LayerNorm) and not m.layernorm.elementwise_affine
+    assert tuple(m.layernorm.normalized_shape) == (24,) and m.eps == m.layernorm.eps == 1e-5
+    assert [n for n, _ in m.named_children()] == ["layernorm"]
 
 
 def test_state_dict_round_trip():

@@ -53,8 +53,10 @@ def test_replace_bitlinear_on_the_real_reference_model(ref_classes):
     n_ref = sum(isinstance(m, BitLinearInf) for m in model.modules())
     assert n_ref == 7 * TINY["num_hidden_layers"]
 
+    ln_before = model.model.layers[0].self_attn.q_proj.layernorm
     assert replace_bitlinear(model) == n_ref
     assert not any(isinstance(m, BitLinearInf) for m in model.modules())
+    assert model.model.layers[0].self_attn.q_proj.layernorm is ln_before  # the reference's nn.LayerNorm attribute is adopted
     for layer in model.model.layers:
         for mod in (layer.self_attn.q_proj, layer.self_attn.k_proj, layer.self_attn.v_proj, layer.self_attn.o_proj,
                     layer.mlp.gate_proj, layer.mlp.up_proj, layer.mlp.down_proj):
