@@ -29,3 +29,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "tok/s" and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+    # both arms print the same `config` object for the same workload; the extrapolation is said out loud
+    import bench
+    assert line["config"] == bench.workload_config("LLaMA-7B-OneBit", 1, 1, False)
+    assert "EXTRAPOLATED" in line["note"] and line["metric"] == bench.METRIC
